@@ -1,0 +1,190 @@
+/*
+ * litegs_b200.h -- C ABI of liblitegs_b200.so, the B200-native (sm_100a) replacement for the hot path of
+ * MooreThreads/LiteGS' `litegs_fused` extension (reference: litegs/submodules/gaussian_raster/, "GR/").
+ *
+ * The reference binds this path through a pybind11 module on at::Tensor (GR/ext_cuda.cpp:9-35); its
+ * 26 entry points are the interface a maintainer re-binds.  Here every entry point is a plain C
+ * function on raw DEVICE pointers, sizes and a CUDA stream handle -- no torch types -- and the
+ * host-side mirror of the pybind surface (litegs_b200/fused.py, same names, same positional
+ * arguments, same return lists) sits above it.  INTEGRATION.md shows the binding stubs.
+ *
+ * Conventions
+ *   - all pointers are device pointers unless a comment says otherwise; layouts are the reference's
+ *     SoA with the point index innermost: [C,N], [V,C,N]; matrices are row-vector style [V,4,4];
+ *   - `valid_length` is a nullable DEVICE int[1]: entries with index >= *valid_length are not computed
+ *     (GPU-driven pipeline, no host sync), exactly as in the reference;
+ *   - `stream` is a cudaStream_t passed as void*; every launch goes to it (the reference launches on
+ *     the legacy default stream);
+ *   - return value: 0 on success, otherwise a cudaError_t value or one of LGS_ERR_*; the message is
+ *     available from lgs_last_error() (thread-local).  Launches are checked.
+ *   - tile sizes: 8x16 (reference default), 12x16, 16x16, 8x8 (GR/raster.cu:375-383).
+ */
+#ifndef LITEGS_B200_H
+#define LITEGS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGS_ERR_ARG 10001
+#define LGS_ERR_WORKSPACE 10002
+#define LGS_REC_FLOATS 12  /* floats per packed splat record  (px py A B | C o r g | b depth - -) */
+#define LGS_GRAD_FLOATS 12 /* floats per gradient accumulator (dmx dmy dA dB | dC dr dg db | do esq - -) */
+
+const char* lgs_last_error(void);
+int lgs_abi_version(void);
+
+/* ---- chunk culling + activation ------------------------------------------------------------------ */
+
+/* replaces frustum_culling_aabb, GR/compact.cu:419-551 (GR/compact.h:33).
+ * aabb_origin/aabb_ext f32[3,M]; frustumplane f32[V,6,4]; visibility u8[M]; visible_num i32[1];
+ * visible_chunk_id i64[M] receives the visible chunk ids in ASCENDING order (first *visible_num valid). */
+int lgs_frustum_culling_aabb(const float* aabb_origin, const float* aabb_ext, const float* frustumplane, int M, int V,
+                             uint8_t* visibility, int* visible_num, int64_t* visible_chunk_id, void* stream);
+
+/* replaces cull_compact_activate, GR/compact.cu:825-893,983-1085 (GR/compact.h:3-8).
+ * params [..,C,S] (C chunks of S points); outputs [..,A,S] with A = allocated chunks:
+ * act_position f32[4,A,S] (w=1), act_scale f32[3,A,S]=exp, act_rotation f32[4,A,S] normalised,
+ * color f32[V,3,A,S] = SH(deg)+0.5 (no clamp), act_opacity f32[1,A,S]=sigmoid, 0 for chunks
+ * >= *visible_chunks_num. */
+int lgs_cull_compact_activate(int sh_degree, const int64_t* visible_chunk_id, const int* visible_chunks_num,
+                              const float* view_matrix, int V, const float* position, const float* scale,
+                              const float* rotation, const float* sh_base, const float* sh_rest, const float* opacity,
+                              int C, int S, int A, float* act_position, float* act_scale, float* act_rotation,
+                              float* color, float* act_opacity, void* stream);
+
+/* replaces activate_backward, GR/compact.cu:895-980,1087-1212 (GR/compact.h:10-16).
+ * true_sigmoid_grad = 0 reproduces the reference's opacity-logit gradient d_o*sigma(x)
+ * (GR/compact.cu:952); 1 gives sigma(1-sigma).  Outputs are compacted [..,A,S];
+ * g_sh_rest f32[rest_dim,3,A,S] is zeroed first. */
+int lgs_activate_backward(int sh_degree, const int64_t* visible_chunk_id, const int* visible_chunks_num,
+                          const float* view_matrix, int V, const float* position, const float* scale,
+                          const float* rotation, const float* opacity, int C, int S, int A, int rest_dim,
+                          int true_sigmoid_grad, const float* g_act_position, const float* g_act_scale,
+                          const float* g_act_rotation, const float* g_color, const float* g_act_opacity,
+                          float* g_position, float* g_scale, float* g_rotation, float* g_sh_base, float* g_sh_rest,
+                          float* g_opacity, void* stream);
+
+/* ---- per-Gaussian projection operators ------------------------------------------------------------- */
+
+/* mvp_transform_forward/backward, GR/transform.cu:378-598 (GR/transform.h:13-18). world f32[4,N] ->
+ * view,ndc f32[V,4,N]; backward sums over views into f32[4,N]. */
+int lgs_mvp_transform_forward(const float* world_position, const float* view_matrix, const float* proj_matrix,
+                              const int* valid_length, int V, int N, float* view_position, float* ndc_position, void* stream);
+int lgs_mvp_transform_backward(const float* grad_ndc_pos, const float* grad_view_pos, const float* view_matrix,
+                               const float* proj_matrix, const float* view_pos, const int* valid_length, int V, int N,
+                               float* grad_world_pos, void* stream);
+
+/* createTransformMatrix_forward/backward, GR/transform.cu:92-256 (GR/transform.h:6-7). quaternion f32[4,N]
+ * (r,x,y,z), scale f32[3,N] -> T = diag(s) R(q) f32[3,3,N]. */
+int lgs_create_transform_matrix_forward(const float* quaternion, const float* scale, const int* valid_length, int N,
+                                        float* transform, void* stream);
+int lgs_create_transform_matrix_backward(const float* transform_grad, const float* quaternion, const float* scale,
+                                         const int* valid_length, int N, float* grad_quaternion, float* grad_scale,
+                                         void* stream);
+
+/* jacobianRayspace, GR/transform.cu:22-90 (GR/transform.h:4). view_pos f32[V,4,N] -> J f32[V,3,3,N]
+ * (all nine rows written, five of them zero). */
+int lgs_jacobian_rayspace(const float* view_pos, const float* proj_matrix, const int* valid_length, int V, int N,
+                          int output_h, int output_w, float* jacobian, void* stream);
+
+/* createCov2dDirectly_forward/backward, GR/transform.cu:736-927 (GR/transform.h:21-22). */
+int lgs_create_cov2d_forward(const float* J, const float* view_matrix, const float* transform_matrix,
+                             const int* valid_length, int V, int N, float* cov2d, void* stream);
+int lgs_create_cov2d_backward(const float* cov2d_grad, const float* J, const float* view_matrix,
+                              const float* transform_matrix, const int* valid_length, int V, int N,
+                              float* transform_matrix_grad, void* stream);
+
+/* eigh_and_inv_2x2matrix_forward / inv_2x2matrix_backward, GR/transform.cu:1364-1518 (GR/transform.h:24-25). */
+int lgs_eigh_and_inv_2x2_forward(const float* input, const int* valid_length, int V, int N, float* val, float* vec,
+                                 float* inv, void* stream);
+int lgs_inv_2x2_backward(const float* inv_matrix, const float* grad_inv, const int* valid_length, int V, int N,
+                         float* grad_matrix, void* stream);
+
+/* sh2rgb_forward/backward, GR/transform.cu:951-1361 (GR/transform.h:23-24): cluster_size=0 path. */
+int lgs_sh2rgb_forward(int degree, const float* sh_base, const float* sh_rest, const float* dirs, int V, int N,
+                       float* rgb, void* stream);
+int lgs_sh2rgb_backward(int degree, const float* rgb_grad, int sh_rest_dim, const float* dirs, int V, int N,
+                        float* sh_base_grad, float* sh_rest_grad, float* dir_grad, void* stream);
+
+/* ---- binning ----------------------------------------------------------------------------------------- */
+
+/* get_allocate_size, GR/binning.cu:289-440 (GR/binning.h:10-14): visibility + exact ellipse/tile overlap
+ * count (GR/speedy_splat.cuh:33-149). left_up/right_down i32[V,2,N], allocate_size i32[V,N] (zeroed). */
+int lgs_get_allocate_size(const float* ndc, const float* view_space_z, const float* inv_cov2d, const float* opacity,
+                          const int* valid_length, int V, int N, int height, int width, int tile_h, int tile_w,
+                          int* left_up, int* right_down, int* allocate_size, void* stream);
+
+/* create_table, GR/binning.cu:33-226 (GR/binning.h:5-9): emit (tile+1, splat) in depth order at `offset`
+ * (inclusive scan, i32[V,N]) then a stable radix sort on the tile bits.  cap = table length; outputs
+ * i32[V,cap].  The reference sizes the table from a pinned feedback buffer (GR/binning.cu:137-163);
+ * that policy lives in the host mirror, the C entry point takes `cap` explicitly. */
+int lgs_create_table_workspace_bytes(int V, int cap, size_t* bytes);
+int lgs_create_table(const float* ndc, const float* inv_cov2d, const float* opacity, const int* offset,
+                     const int64_t* depth_sorted_pointid, int V, int N, int cap, int height, int width, int tile_h,
+                     int tile_w, int* sorted_tile_id, int* sorted_point_id, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* tileRange, GR/binning.cu:228-287 (GR/binning.h:9). tile_range i32[V,max_tile_id+2], -1 = empty.
+ * fix_last=1 closes the last populated tile (the reference leaves it open: SURVEY Q3); 0 = bit-compatible. */
+int lgs_tile_range(const int* table_tile_id, int V, int table_length, int max_tile_id, int fix_last, int* tile_range,
+                   void* stream);
+
+/* building blocks of the fused pipeline (cub radix sort / scan on the caller's stream and workspace) */
+int lgs_sort_pairs_u32_workspace_bytes(int n, size_t* bytes);
+int lgs_sort_pairs_u32(const unsigned* keys_in, unsigned* keys_out, const unsigned* vals_in, unsigned* vals_out, int n,
+                       int begin_bit, int end_bit, void* workspace, size_t workspace_bytes, void* stream);
+int lgs_scan_gathered_workspace_bytes(int n, size_t* bytes);
+int lgs_scan_gathered(const int* counts, const unsigned* order, int n, int* out, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* ---- rasterisation ------------------------------------------------------------------------------------- */
+
+/* pack_forward_params, GR/raster.cu:334-356 -> packed f32[V,N,12] (fp32 record, see LGS_REC_FLOATS). */
+int lgs_pack_params(const float* ndc, const float* cov2d_inv, const float* color, const float* opacity, int V, int N,
+                    int img_h, int img_w, float* packed_params, void* stream);
+
+/* rasterize_forward(_packed), GR/raster.cu:161-332,386-586 (GR/raster.h:3-33).  Images are padded to
+ * whole tiles: img f32[V,3,Hp,Wp], transmittance f32[V,1,Hp,Wp], last_contributor i16[V,1,Hp,Wp];
+ * fragment_count i32[V,1,N] / fragment_weight f32[V,1,N] are accumulated when enable_statistic (caller
+ * zeroes them).  specific_tiles i32[V,n_specific] (1-based tile ids, 0 = skip) or NULL. */
+int lgs_rasterize_forward_packed(const int* sorted_points, const int* start_index, const float* packed_params,
+                                 const int* specific_tiles, int n_specific, int V, int N, int cap, int img_h, int img_w,
+                                 int tile_h, int tile_w, int enable_statistic, float* img, float* transmittance,
+                                 short* last_contributor, int* fragment_count, float* fragment_weight, void* stream);
+
+/* rasterize_backward, GR/raster.cu:599-886,917-1037 (GR/raster.h:35-50).  packed_grad f32[V,N,12] is
+ * scratch (zeroed here); d_trans_img and grad_inv_scaler (DEVICE f32[1]) may be NULL.  Outputs d_ndc
+ * f32[V,4,N], d_cov2d_inv f32[V,2,2,N], d_color f32[V,3,N], d_opacity f32[1,N] (view 0 only, as the
+ * reference), err_sum/err_square_sum f32[V,1,N].  Pass d_ndc=NULL to skip the unpack (fused path). */
+int lgs_rasterize_backward(const int* sorted_points, const int* start_index, const float* packed_params,
+                           const int* specific_tiles, int n_specific, const float* final_transmittance,
+                           const short* last_contributor, const float* d_img, const float* d_trans_img,
+                           const float* grad_inv_scaler, int V, int N, int cap, int img_h, int img_w, int tile_h,
+                           int tile_w, int enable_statistic, float* packed_grad, float* d_ndc, float* d_cov2d_inv,
+                           float* d_color, float* d_opacity, float* err_sum, float* err_square_sum, void* stream);
+
+/* staging selector for the raster kernels: 1 = cp.async.bulk + mbarrier (default), 0 = cp.async */
+int lgs_set_staging(int bulk);
+
+/* ---- optimiser / statistics (next rows) ------------------------------------------------------ */
+
+/* adamUpdate, GR/compact.cu:320-417 (GR/compact.h:18-23): Adam WITHOUT bias correction. */
+int lgs_adam_update_chunk(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                          const int64_t* visible_index, const int* valid_length, int R, int C, int S, int A, double lr,
+                          double b1, double b2, double eps, void* stream);
+int lgs_adam_update_primitive(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                              const int64_t* primitive_visible, int R, int N, double lr, double b1, double b2,
+                              double eps, void* stream);
+
+/* gpu_driven_pipeline_sparse_op, GR/compact.cu:1221-1336 (GR/compact.h:35-41). dtype 0=f32 1=i32; op 0=add 1=min 2=max */
+int lgs_sparse_chunk_op(void* A, const void* B, const int64_t* visible_chunk_ids, const int* visible_count, int dtype,
+                        int op, int ele_num, int chunks, int alloc_chunks, int chunk_size, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LITEGS_B200_H */

@@ -1,0 +1,244 @@
+// binning.cu -- visibility + exact tile-overlap count, (tile, splat) pair emission in depth order,
+// stable radix sort on the tile bits, tile ranges.      replaces GR/binning.cu (all of it)
+//
+// Ordering scheme (the reference's, because it moves the fewest bytes when pairs >> splats): splats are
+// depth-sorted once (N keys), pairs are emitted in that order at scanned offsets, then ONE stable LSD
+// radix sort over only the ceil(log2(tiles))+1 tile bits (2 passes at 1080p) groups them by tile while
+// preserving depth order.  cub::DeviceRadixSort (CCCL, header-only) provides the onesweep passes.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include "common.cuh"
+#include "splat_geom.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// per-splat pixel bbox + tile count.                                  replaces GR/binning.cu:289-440
+// ------------------------------------------------------------------------------------------------
+template <int TH, int TW>
+__global__ void __launch_bounds__(256) allocate_size_kernel(
+    const float* __restrict__ ndc, const float* __restrict__ viewz, const float* __restrict__ inv_cov,
+    const float* __restrict__ opac, const int* __restrict__ valid_length, int N, int H, int W, int gx, int gy,
+    int* __restrict__ left_up, int* __restrict__ right_down, int* __restrict__ alloc)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (i >= N || (valid_length != nullptr && i >= valid_length[0])) return;
+    size_t o4 = (size_t)b * 4 * N + i, o2 = (size_t)b * 2 * N + i;
+    SplatGeom g;
+    lgs_splat_setup<TH, TW>(ndc[o4], ndc[o4 + N], viewz[(size_t)b * N + i], inv_cov[o4], inv_cov[o4 + N],
+                            inv_cov[o4 + 3 * (size_t)N], opac[i], H, W, gx, gy, true, g);
+    if (g.visible) {
+        left_up[o2] = lgs_f2i_rz(ceilf(g.bbox_min[0])); left_up[o2 + N] = lgs_f2i_rz(ceilf(g.bbox_min[1]));
+        right_down[o2] = lgs_f2i_rz(floorf(g.bbox_max[0])); right_down[o2 + N] = lgs_f2i_rz(floorf(g.bbox_max[1]));
+        alloc[(size_t)b * N + i] = lgs_process_tiles<TH, TW, false>(g, gx, i, 0, 0, nullptr, nullptr);
+    } else {
+        left_up[o2] = -1; left_up[o2 + N] = -1; right_down[o2] = -1; right_down[o2 + N] = -1;
+        alloc[(size_t)b * N + i] = 0;
+    }
+}
+
+extern "C" int lgs_get_allocate_size(const float* ndc, const float* view_space_z, const float* inv_cov2d, const float* opacity,
+                                     const int* valid_length, int V, int N, int height, int width, int tile_h, int tile_w,
+                                     int* left_up, int* right_down, int* allocate_size, void* stream)
+{
+    LGS_REQUIRE(lgs_tile_ok(tile_h, tile_w), "get_allocate_size: tile %dx%d not one of 8x16, 12x16, 16x16, 8x8", tile_h, tile_w);
+    LGS_REQUIRE(V >= 1 && N >= 0, "get_allocate_size: bad sizes V=%d N=%d", V, N);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N == 0) return LGS_OK;
+    // entries past valid_length read as 0 (the reference allocates the counts with torch::zeros)
+    LGS_CUDA(cudaMemsetAsync(allocate_size, 0, sizeof(int) * (size_t)V * N, st));
+    int gx = (width + tile_w - 1) / tile_w, gy = (height + tile_h - 1) / tile_h;
+    dim3 grid(lgs_cdiv(N, 256), V);
+    LGS_DISPATCH_TILE(tile_h, tile_w,
+        allocate_size_kernel<TH, TW><<<grid, 256, 0, st>>>(ndc, view_space_z, inv_cov2d, opacity, valid_length, N, height, width,
+                                                          gx, gy, left_up, right_down, allocate_size);)
+    LGS_CHECK_LAUNCH("allocate_size_kernel");
+    return LGS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// emit (tile+1, splat) pairs in depth order.                          replaces GR/binning.cu:33-110
+// ------------------------------------------------------------------------------------------------
+template <int TH, int TW>
+__global__ void __launch_bounds__(256) emit_pairs_kernel(
+    const float* __restrict__ ndc, const float* __restrict__ inv_cov, const float* __restrict__ opac,
+    const int* __restrict__ offset /*inclusive scan, depth order*/, const int64_t* __restrict__ sorted_id,
+    int N, int cap, int H, int W, int gx, int gy, int* __restrict__ keys, int* __restrict__ vals)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (j >= N) return;
+    int off = j == 0 ? 0 : offset[(size_t)b * N + j - 1];
+    int asz = offset[(size_t)b * N + j] - off;
+    if (asz <= 0 || off + asz > cap) return;   // overflow beyond the allocation is dropped (GR/binning.cu:63)
+    int i = (int)sorted_id[(size_t)b * N + j];
+    size_t o4 = (size_t)b * 4 * N + i;
+    SplatGeom g;
+    lgs_splat_setup<TH, TW>(ndc[o4], ndc[o4 + N], 1.0f, inv_cov[o4], inv_cov[o4 + N], inv_cov[o4 + 3 * (size_t)N], opac[i],
+                            H, W, gx, gy, false, g);
+    if (g.visible) lgs_process_tiles<TH, TW, true>(g, gx, i, off, cap, keys + (size_t)b * cap, vals + (size_t)b * cap);
+}
+
+static inline int tile_bits(int tiles)
+{
+    int bit = 0;
+    unsigned t = (unsigned)tiles;
+    while (t >>= 1) bit++;
+    return bit + 1;     // GR/binning.cu:199-202
+}
+
+extern "C" int lgs_create_table_workspace_bytes(int V, int cap, size_t* bytes)
+{
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs<int, int>(nullptr, tmp, nullptr, nullptr, nullptr, nullptr, cap, 0, 32);
+    *bytes = ((tmp + 255) / 256) * 256 + 2 * sizeof(int) * (size_t)V * cap + 512;
+    return LGS_OK;
+}
+
+// offset: inclusive scan of the depth-ordered counts [V,N]; depth_sorted_pointid int64 [V,N];
+// outputs sorted_tile_id / sorted_point_id int32 [V,cap].
+extern "C" int lgs_create_table(const float* ndc, const float* inv_cov2d, const float* opacity, const int* offset,
+                                const int64_t* depth_sorted_pointid, int V, int N, int cap, int height, int width, int tile_h,
+                                int tile_w, int* sorted_tile_id, int* sorted_point_id, void* workspace, size_t workspace_bytes,
+                                void* stream)
+{
+    LGS_REQUIRE(lgs_tile_ok(tile_h, tile_w), "create_table: tile %dx%d not one of 8x16, 12x16, 16x16, 8x8", tile_h, tile_w);
+    LGS_REQUIRE(cap > 0, "create_table: error pred_allocate_size (%d)", cap);
+    size_t need = 0;
+    lgs_create_table_workspace_bytes(V, cap, &need);
+    if (workspace == nullptr || workspace_bytes < need) {
+        lgs_set_error("create_table: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
+        return LGS_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    int* keys = (int*)ws;
+    int* vals = keys + (size_t)V * cap;
+    void* cub_tmp = (void*)(((uintptr_t)(vals + (size_t)V * cap) + 255) & ~(uintptr_t)255);
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs<int, int>(nullptr, cub_bytes, nullptr, nullptr, nullptr, nullptr, cap, 0, 32);
+    // unused slots keep key 0 and sort to the front
+    LGS_CUDA(cudaMemsetAsync(keys, 0, sizeof(int) * (size_t)V * cap, st));
+    LGS_CUDA(cudaMemsetAsync(vals, 0, sizeof(int) * (size_t)V * cap, st));
+    int gx = (width + tile_w - 1) / tile_w, gy = (height + tile_h - 1) / tile_h;
+    if (N > 0) {
+        dim3 grid(lgs_cdiv(N, 256), V);
+        LGS_DISPATCH_TILE(tile_h, tile_w,
+            emit_pairs_kernel<TH, TW><<<grid, 256, 0, st>>>(ndc, inv_cov2d, opacity, offset, depth_sorted_pointid, N, cap, height,
+                                                           width, gx, gy, keys, vals);)
+        LGS_CHECK_LAUNCH("emit_pairs_kernel");
+    }
+    int bits = tile_bits(gx * gy);
+    for (int b = 0; b < V; b++) {
+        LGS_CUDA(cub::DeviceRadixSort::SortPairs<int, int>(cub_tmp, cub_bytes, keys + (size_t)b * cap, sorted_tile_id + (size_t)b * cap,
+                                                           vals + (size_t)b * cap, sorted_point_id + (size_t)b * cap, cap, 0, bits, st));
+    }
+    return LGS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tile ranges.                                                        replaces GR/binning.cu:228-287
+// range[t] = first index of key t or -1; range[t+1] is the end marker.  fix_last closes the last
+// populated tile, which the reference leaves open so that it renders empty.
+// ------------------------------------------------------------------------------------------------
+__global__ void fill_int_kernel(int* __restrict__ p, int v, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__global__ void tile_range_kernel(const int* __restrict__ keys, int L, int max_tile, int fix_last, int* __restrict__ range)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    const int* k = keys + (size_t)b * L;
+    int* r = range + (size_t)b * (max_tile + 2);
+    if (j >= L) return;
+    int cur = k[j];
+    if (j == 0) r[cur] = 0;
+    if (j == L - 1) {
+        r[max_tile + 1] = L;
+        if (fix_last && cur + 1 <= max_tile + 1) r[cur + 1] = L;
+    } else {
+        int nxt = k[j + 1];
+        if (cur != nxt) {
+            if (cur + 1 < nxt) r[cur + 1] = j + 1;
+            r[nxt] = j + 1;
+        }
+    }
+}
+
+extern "C" int lgs_tile_range(const int* table_tile_id, int V, int table_length, int max_tile_id, int fix_last, int* tile_range,
+                              void* stream)
+{
+    LGS_REQUIRE(V >= 1 && table_length >= 0 && max_tile_id >= 0, "tileRange: bad sizes V=%d L=%d max_tile=%d", V, table_length, max_tile_id);
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t n = (size_t)V * (max_tile_id + 2);
+    fill_int_kernel<<<lgs_cdiv((long long)n, 256), 256, 0, st>>>(tile_range, -1, n);
+    LGS_CHECK_LAUNCH("fill_int_kernel");
+    if (table_length > 0) {
+        tile_range_kernel<<<dim3(lgs_cdiv(table_length, 512), V), 512, 0, st>>>(table_tile_id, table_length, max_tile_id, fix_last, tile_range);
+        LGS_CHECK_LAUNCH("tile_range_kernel");
+    }
+    return LGS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// building blocks for the fused pipeline: u32 radix sort and "gather + inclusive scan".
+// ------------------------------------------------------------------------------------------------
+extern "C" int lgs_sort_pairs_u32_workspace_bytes(int n, size_t* bytes)
+{
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs<unsigned, unsigned>(nullptr, tmp, nullptr, nullptr, nullptr, nullptr, n, 0, 32);
+    *bytes = tmp + 256;
+    return LGS_OK;
+}
+
+extern "C" int lgs_sort_pairs_u32(const unsigned* keys_in, unsigned* keys_out, const unsigned* vals_in, unsigned* vals_out, int n,
+                                  int begin_bit, int end_bit, void* workspace, size_t workspace_bytes, void* stream)
+{
+    if (n <= 0) return LGS_OK;
+    size_t need = 0;
+    cub::DeviceRadixSort::SortPairs<unsigned, unsigned>(nullptr, need, nullptr, nullptr, nullptr, nullptr, n, begin_bit, end_bit);
+    void* ws = (void*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    if (workspace == nullptr || workspace_bytes < need + 256) {
+        lgs_set_error("sort_pairs_u32: workspace of %zu bytes needed, %zu given", need + 256, workspace_bytes);
+        return LGS_ERR_WORKSPACE;
+    }
+    LGS_CUDA(cub::DeviceRadixSort::SortPairs<unsigned, unsigned>(ws, need, keys_in, keys_out, vals_in, vals_out, n, begin_bit, end_bit,
+                                                                 (cudaStream_t)stream));
+    return LGS_OK;
+}
+
+struct GatherCount {
+    const int* counts; const unsigned* order;
+    __host__ __device__ int operator()(int j) const { return counts[order[j]]; }
+};
+
+extern "C" int lgs_scan_gathered_workspace_bytes(int n, size_t* bytes)
+{
+    size_t tmp = 0;
+    cub::CountingInputIterator<int> cnt(0);
+    GatherCount op{ nullptr, nullptr };
+    cub::TransformInputIterator<int, GatherCount, cub::CountingInputIterator<int>> it(cnt, op);
+    cub::DeviceScan::InclusiveSum(nullptr, tmp, it, (int*)nullptr, n);
+    *bytes = tmp + 256;
+    return LGS_OK;
+}
+
+// out[j] = sum_{k<=j} counts[order[k]]   (inclusive, int32)
+extern "C" int lgs_scan_gathered(const int* counts, const unsigned* order, int n, int* out, void* workspace, size_t workspace_bytes,
+                                 void* stream)
+{
+    if (n <= 0) return LGS_OK;
+    cub::CountingInputIterator<int> cnt(0);
+    GatherCount op{ counts, order };
+    cub::TransformInputIterator<int, GatherCount, cub::CountingInputIterator<int>> it(cnt, op);
+    size_t need = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, need, it, out, n);
+    void* ws = (void*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    if (workspace == nullptr || workspace_bytes < need + 256) {
+        lgs_set_error("scan_gathered: workspace of %zu bytes needed, %zu given", need + 256, workspace_bytes);
+        return LGS_ERR_WORKSPACE;
+    }
+    LGS_CUDA(cub::DeviceScan::InclusiveSum(ws, need, it, out, n, (cudaStream_t)stream));
+    return LGS_OK;
+}

@@ -1,0 +1,538 @@
+// raster.cu -- per-tile front-to-back alpha compositing and the matching back-to-front backward.
+//                                                                 replaces GR/raster.cu (all of it)
+//
+// Design (B200 / sm_100a, no tensor-core work: there is no dense contraction here):
+//  * one warp owns one tile (8x16, 12x16, 16x16 or 8x8 pixels); a lane owns a column strip of
+//    PPT = TH*TW/32 pixels, so the splat's quadratic form is evaluated with dx fixed per lane and two
+//    FMAs per pixel; transmittance, colour and the contributor count live in registers;
+//  * the tile's depth-sorted splat list is consumed in chunks of 32: lane i fetches id i of the chunk
+//    (one coalesced 128-byte row of the index list) and stages that splat's 48-byte fp32 record into
+//    shared memory with an asynchronous copy -- either three 16-byte cp.async (LDGSTS) or one 48-byte
+//    cp.async.bulk (UBLKCP, the TMA engine's 1-D bulk copy) completing on an mbarrier; two buffers per
+//    warp, so chunk c+1 is in flight while chunk c is blended; records are then read back as
+//    conflict-free broadcast LDS.128;
+//  * fp32 throughout (ex2.approx.ftz for the Gaussian): the 1e-4 parity gate of BASELINE.json rules out
+//    the reference's packed-half blend;
+//  * backward: per-(tile, splat) gradients are reduced over the tile's pixels entirely inside the warp
+//    (per-lane polynomial moments in dy, then a 9-shuffle transposing butterfly for 8 values) and
+//    leave the SM exactly once, as one predicated RED.ADD.F32 touching a single 48-byte record.
+#include "common.cuh"
+
+#define FULL_MASK 0xffffffffu
+#define LOG2E 1.4426950408889634f
+#define ALPHA_MIN (1.0f / 256.0f)
+#define ALPHA_MAX (255.0f / 256.0f)
+#define T_MIN (1.0f / 8192.0f)
+#define WARPS_PER_BLOCK 4
+
+__device__ __forceinline__ float fast_ex2(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_rcp(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ---- asynchronous staging primitives -------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(dst)), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes));
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP); bytes % 16 == 0, 16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Per-warp chunk stager.  BULK selects cp.async.bulk + mbarrier, otherwise cp.async (LDGSTS) groups.
+template <bool BULK>
+struct Stager {
+    SplatRec* buf;       // [2][32] records of this warp
+    uint64_t* bar;       // [2] mbarriers of this warp (BULK only)
+    unsigned phase_bits; // bit w = parity to wait for on buffer w
+    unsigned pending;    // bit w = a copy into buffer w is in flight (must land before the CTA retires)
+    int lane;
+    __device__ __forceinline__ void init(SplatRec* b, uint64_t* m, int ln)
+    {
+        buf = b; bar = m; lane = ln; phase_bits = 0; pending = 0;
+        if (BULK) {
+            if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+            __syncwarp();
+        }
+    }
+    // lane `lane` stages record `id` (or nothing when id < 0) into slot `lane` of buffer `which`.
+    __device__ __forceinline__ void issue(int which, const SplatRec* __restrict__ recs, int id)
+    {
+        SplatRec* dst = buf + which * 32 + lane;
+        if (BULK) {
+            unsigned live = __ballot_sync(FULL_MASK, id >= 0);
+            if (lane == 0) mbar_expect_tx(&bar[which], (unsigned)__popc(live) * (unsigned)sizeof(SplatRec));
+            __syncwarp();
+            if (id >= 0) bulk_g2s(dst, recs + id, (unsigned)sizeof(SplatRec), &bar[which]);
+            pending |= (1u << which);
+        } else {
+            if (id >= 0) {
+                const char* src = (const char*)(recs + id);
+                cp_async16((char*)dst, src);
+                cp_async16((char*)dst + 16, src + 16);
+                cp_async16((char*)dst + 32, src + 32);
+            }
+            cp_async_commit();
+        }
+    }
+    // wait until buffer `which` has landed; `more_in_flight` tells whether a younger group exists.
+    __device__ __forceinline__ void wait(int which, bool more_in_flight)
+    {
+        if (BULK) {
+            mbar_wait(&bar[which], (phase_bits >> which) & 1u);
+            phase_bits ^= (1u << which);
+            pending &= ~(1u << which);
+        } else {
+            if (more_in_flight) cp_async_wait<1>(); else cp_async_wait<0>();
+            __syncwarp();
+        }
+    }
+    // nothing may still be writing this CTA's shared memory when the warp leaves
+    __device__ __forceinline__ void drain()
+    {
+        if (BULK) {
+            if (pending & 1u) wait(0, false);
+            if (pending & 2u) wait(1, false);
+        } else {
+            cp_async_wait<0>();
+        }
+    }
+};
+
+// ---- pack ------------------------------------------------------------------------------------------
+// SoA -> 48-byte record.  Screen mean as in GR/raster.cu:347-348, single-rounded ops so that the CPU
+// oracle reproduces the coordinates bit for bit.
+__global__ void pack_kernel(const float* __restrict__ ndc, const float* __restrict__ inv_cov, const float* __restrict__ color,
+                            const float* __restrict__ opac, SplatRec* __restrict__ recs, int N, int H, int W)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (i >= N) return;
+    size_t o4 = (size_t)b * 4 * N + i, o3 = (size_t)b * 3 * N + i;
+    SplatRec r;
+    r.px = __fsub_rn(__fmul_rn(__fmul_rn(__fadd_rn(ndc[o4], 1.0f), 0.5f), (float)W), 0.5f);
+    r.py = __fsub_rn(__fmul_rn(__fmul_rn(__fadd_rn(ndc[o4 + N], 1.0f), 0.5f), (float)H), 0.5f);
+    r.depth = ndc[o4 + 2 * (size_t)N];
+    r.A = inv_cov[o4]; r.B = inv_cov[o4 + N]; r.C = inv_cov[o4 + 3 * (size_t)N];
+    r.o = opac[i];
+    r.r = color[o3]; r.g = color[o3 + N]; r.b = color[o3 + 2 * (size_t)N];
+    r.pad0 = 0.f; r.pad1 = 0.f;
+    recs[(size_t)b * N + i] = r;
+}
+
+// ---- forward ---------------------------------------------------------------------------------------
+template <int TH, int TW, bool STAT, bool BULK>
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_forward_kernel(
+    const int* __restrict__ sorted, const int* __restrict__ start_index, const SplatRec* __restrict__ recs,
+    const int* __restrict__ tiles, int n_sel, float* __restrict__ img, float* __restrict__ Tout, short* __restrict__ last,
+    int* __restrict__ frag_count, float* __restrict__ frag_weight, int gx, int ntile, int cap, int N, int Hp, int Wp)
+{
+    constexpr int PPT = TH * TW / 32;
+    __shared__ __align__(128) SplatRec s_rec[WARPS_PER_BLOCK][2][32];
+    __shared__ __align__(8) uint64_t s_bar[WARPS_PER_BLOCK][2];
+    const int lane = threadIdx.x, warp = threadIdx.y, b = blockIdx.y;
+    const int slot = blockIdx.x * WARPS_PER_BLOCK + warp;
+    int tile_id;
+    if (tiles != nullptr) tile_id = (slot < n_sel) ? tiles[(size_t)b * n_sel + slot] : 0;
+    else tile_id = slot + 1;
+    if (tile_id <= 0 || tile_id > ntile) return;
+
+    const int* rg = start_index + (size_t)b * (ntile + 2);
+    const int start = rg[tile_id];
+    int count = (start < 0) ? 0 : (rg[tile_id + 1] - start);
+    if (count < 0) count = 0;
+    recs += (size_t)b * N;
+    const int* ids = sorted + (size_t)b * cap + (start < 0 ? 0 : start);
+
+    const int x = ((tile_id - 1) % gx) * TW + lane % TW;
+    const int y0 = ((tile_id - 1) / gx) * TH + (lane / TW) * PPT;
+    const float fx = (float)x, fy0 = (float)y0;
+
+    float T[PPT], Cr[PPT], Cg[PPT], Cb[PPT];
+    int n[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; j++) { T[j] = 1.0f; Cr[j] = Cg[j] = Cb[j] = 0.0f; n[j] = 0; }
+
+    if (count > 0) {
+        Stager<BULK> st;
+        st.init(&s_rec[warp][0][0], &s_bar[warp][0], lane);
+        const int nchunks = (count + 31) >> 5;
+        int id_cur = (lane < count) ? ids[lane] : -1;
+        st.issue(0, recs, id_cur);
+        int id_next = (32 + lane < count) ? ids[32 + lane] : -1;
+        bool done = false;
+        for (int c = 0; c < nchunks && !done; c++) {
+            const bool more = (c + 1 < nchunks);
+            if (more) {
+                st.issue((c + 1) & 1, recs, id_next);
+                int nn = (c + 2) * 32 + lane;
+                id_next = (nn < count) ? ids[nn] : -1;
+            }
+            st.wait(c & 1, more);
+            const SplatRec* chunk = &s_rec[warp][c & 1][0];
+            const int nk = min(32, count - c * 32);
+            int my_id = 0;
+            if (STAT) my_id = ids[c * 32 + min(lane, nk - 1)];
+            for (int k = 0; k < nk; k++) {
+                bool lane_active = false;
+#pragma unroll
+                for (int j = 0; j < PPT; j++) lane_active |= (T[j] > T_MIN);
+                if (!__any_sync(FULL_MASK, lane_active)) { done = true; break; }
+                const float4 q0 = *reinterpret_cast<const float4*>(&chunk[k].px);   // px py A B
+                const float4 q1 = *reinterpret_cast<const float4*>(&chunk[k].C);    // C o r g
+                const float cb = chunk[k].b;
+                const float dx = q0.x - fx, dy0 = q0.y - fy0;
+                const float a2 = (-0.5f * LOG2E) * q0.z, b2 = (-LOG2E) * q0.w, c2 = (-0.5f * LOG2E) * q1.x;
+                const float base = a2 * dx * dx, lin = b2 * dx;
+                int fcount = 0; float wsum = 0.f;
+#pragma unroll
+                for (int j = 0; j < PPT; j++) {
+                    const float dy = dy0 - (float)j;
+                    const float pw = fmaf(dy, fmaf(c2, dy, lin), base);
+                    float alpha = q1.y * fast_ex2(pw);
+                    const bool act = T[j] > T_MIN;
+                    n[j] += act ? 1 : 0;
+                    const bool ok = act && (alpha >= ALPHA_MIN);
+                    alpha = fminf(alpha, ALPHA_MAX);
+                    const float w = ok ? alpha * T[j] : 0.0f;
+                    Cr[j] = fmaf(q1.z, w, Cr[j]);
+                    Cg[j] = fmaf(q1.w, w, Cg[j]);
+                    Cb[j] = fmaf(cb, w, Cb[j]);
+                    T[j] -= w;
+                    if (STAT) { fcount += ok ? 1 : 0; wsum += w; }
+                }
+                if (STAT) {
+                    // per-(tile,splat) fragment statistics for densification (GR/raster.cu:288-301)
+                    fcount = __reduce_add_sync(FULL_MASK, fcount);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(FULL_MASK, wsum, o);
+                    int pid = __shfl_sync(FULL_MASK, my_id, k);
+                    if (lane == 0 && fcount > 0) {
+                        atomicAdd(&frag_count[(size_t)b * N + pid], fcount);
+                        atomicAdd(&frag_weight[(size_t)b * N + pid], wsum);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        st.drain();
+    }
+
+    const size_t plane = (size_t)Hp * Wp;
+#pragma unroll
+    for (int j = 0; j < PPT; j++) {
+        const size_t po = (size_t)(y0 + j) * Wp + x;
+        img[((size_t)b * 3 + 0) * plane + po] = fminf(Cr[j], 1.0f);
+        img[((size_t)b * 3 + 1) * plane + po] = fminf(Cg[j], 1.0f);
+        img[((size_t)b * 3 + 2) * plane + po] = fminf(Cb[j], 1.0f);
+        Tout[(size_t)b * plane + po] = T[j];
+        last[(size_t)b * plane + po] = (short)n[j];
+    }
+}
+
+// ---- backward --------------------------------------------------------------------------------------
+// Transposing butterfly: reduces 8 per-lane values over the warp with 9 shuffles.  On return lane L
+// holds the warp total of value index ((L>>4)&1)*4 + ((L>>3)&1)*2 + ((L>>2)&1).
+__device__ __forceinline__ float butterfly8(const float (&v)[8], int lane)
+{
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+    float u[4], w[2];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float send = h16 ? v[i] : v[i + 4], keep = h16 ? v[i + 4] : v[i];
+        u[i] = keep + __shfl_xor_sync(FULL_MASK, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        float send = h8 ? u[i] : u[i + 2], keep = h8 ? u[i + 2] : u[i];
+        w[i] = keep + __shfl_xor_sync(FULL_MASK, send, 8);
+    }
+    float send = h4 ? w[0] : w[1], keep = h4 ? w[1] : w[0];
+    float z = keep + __shfl_xor_sync(FULL_MASK, send, 4);
+    z += __shfl_xor_sync(FULL_MASK, z, 2);
+    z += __shfl_xor_sync(FULL_MASK, z, 1);
+    return z;
+}
+
+template <int TH, int TW, bool STAT, bool TRANS, bool BULK>
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_kernel(
+    const int* __restrict__ sorted, const int* __restrict__ start_index, const SplatRec* __restrict__ recs,
+    const int* __restrict__ tiles, int n_sel, const float* __restrict__ Tfinal, const short* __restrict__ last,
+    const float* __restrict__ d_img, const float* __restrict__ d_trans, float* __restrict__ grad, int gx, int ntile, int cap,
+    int N, int Hp, int Wp)
+{
+    constexpr int PPT = TH * TW / 32;
+    __shared__ __align__(128) SplatRec s_rec[WARPS_PER_BLOCK][2][32];
+    __shared__ __align__(8) uint64_t s_bar[WARPS_PER_BLOCK][2];
+    const int lane = threadIdx.x, warp = threadIdx.y, b = blockIdx.y;
+    const int slot = blockIdx.x * WARPS_PER_BLOCK + warp;
+    int tile_id;
+    if (tiles != nullptr) tile_id = (slot < n_sel) ? tiles[(size_t)b * n_sel + slot] : 0;
+    else tile_id = slot + 1;
+    if (tile_id <= 0 || tile_id > ntile) return;
+    const int* rg = start_index + (size_t)b * (ntile + 2);
+    const int start = rg[tile_id];
+    if (start < 0) return;
+    recs += (size_t)b * N;
+    grad += (size_t)b * N * LGS_GRAD_FLOATS;
+    const int* ids = sorted + (size_t)b * cap + start;
+
+    const int x = ((tile_id - 1) % gx) * TW + lane % TW;
+    const int y0 = ((tile_id - 1) / gx) * TH + (lane / TW) * PPT;
+    const float fx = (float)x, fy0 = (float)y0;
+    const size_t plane = (size_t)Hp * Wp;
+
+    float T[PPT], g0[PPT], g1[PPT], g2[PPT], R0[PPT], R1[PPT], R2[PPT], gt[PPT];
+    int nl[PPT];
+    int kmax = 0;
+#pragma unroll
+    for (int j = 0; j < PPT; j++) {
+        const size_t po = (size_t)(y0 + j) * Wp + x;
+        T[j] = Tfinal[(size_t)b * plane + po];
+        g0[j] = d_img[((size_t)b * 3 + 0) * plane + po];
+        g1[j] = d_img[((size_t)b * 3 + 1) * plane + po];
+        g2[j] = d_img[((size_t)b * 3 + 2) * plane + po];
+        gt[j] = TRANS ? d_trans[(size_t)b * plane + po] * T[j] : 0.0f;   // dL/dT_final * T_final
+        R0[j] = R1[j] = R2[j] = 0.0f;
+        nl[j] = (int)last[(size_t)b * plane + po];
+        kmax = max(kmax, nl[j]);
+    }
+    kmax = __reduce_max_sync(FULL_MASK, kmax);
+    if (kmax <= 0) return;
+
+    Stager<BULK> st;
+    st.init(&s_rec[warp][0][0], &s_bar[warp][0], lane);
+    const int nchunks = (kmax + 31) >> 5;
+    // chunks are visited from the back: chunk index c = nchunks-1 ... 0, buffer parity by visit order
+    int c0 = nchunks - 1;
+    int id_cur = (c0 * 32 + lane < kmax) ? ids[c0 * 32 + lane] : -1;
+    st.issue(0, recs, id_cur);
+    int id_next = (c0 >= 1) ? ids[(c0 - 1) * 32 + lane] : -1;
+    for (int v = 0; v < nchunks; v++) {
+        const int c = nchunks - 1 - v;
+        const bool more = (c >= 1);
+        const int id_this = id_cur;
+        if (more) {
+            st.issue((v + 1) & 1, recs, id_next);
+            id_cur = id_next;
+            id_next = (c >= 2) ? ids[(c - 2) * 32 + lane] : -1;
+        }
+        st.wait(v & 1, more);
+        const SplatRec* chunk = &s_rec[warp][v & 1][0];
+        const int nk = min(32, kmax - c * 32);
+        for (int kk = nk - 1; kk >= 0; kk--) {
+            const int k = c * 32 + kk;
+            const float4 q0 = *reinterpret_cast<const float4*>(&chunk[kk].px);   // px py A B
+            const float4 q1 = *reinterpret_cast<const float4*>(&chunk[kk].C);    // C o r g
+            const float cb = chunk[kk].b;
+            const float dx = q0.x - fx, dy0 = q0.y - fy0;
+            const float a2 = (-0.5f * LOG2E) * q0.z, b2 = (-LOG2E) * q0.w, c2 = (-0.5f * LOG2E) * q1.x;
+            const float base = a2 * dx * dx, lin = b2 * dx;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, dr = 0.f, dg = 0.f, db = 0.f, dop = 0.f, esq = 0.f;
+            bool any = false;
+#pragma unroll
+            for (int j = 0; j < PPT; j++) {
+                const float dy = dy0 - (float)j;
+                const float pw = fmaf(dy, fmaf(c2, dy, lin), base);
+                const float G = fast_ex2(pw);
+                const float at = q1.y * G;
+                if (k < nl[j] && at >= ALPHA_MIN) {
+                    any = true;
+                    const float a = fminf(at, ALPHA_MAX);
+                    const float rc = fast_rcp(1.0f - a);
+                    const float Tj = fminf(1.0f, T[j] * rc);      // transmittance in front of this splat
+                    T[j] = Tj;
+                    const float w = a * Tj;
+                    dr = fmaf(w, g0[j], dr); dg = fmaf(w, g1[j], dg); db = fmaf(w, g2[j], db);
+                    float da = Tj * ((q1.z - R0[j]) * g0[j] + (q1.w - R1[j]) * g1[j] + (cb - R2[j]) * g2[j]);
+                    if (TRANS) da -= gt[j] * rc;
+                    R0[j] = fmaf(a, q1.z - R0[j], R0[j]);
+                    R1[j] = fmaf(a, q1.w - R1[j], R1[j]);
+                    R2[j] = fmaf(a, cb - R2[j], R2[j]);
+                    const float go = G * da;
+                    dop += go;
+                    if (STAT) esq = fmaf(go, go, esq);
+                    const float dpw = at * da;          // passes through the 255/256 clamp (GR/raster.cu:776-778)
+                    s0 += dpw; s1 = fmaf(dpw, dy, s1); s2 = fmaf(dpw * dy, dy, s2);
+                }
+            }
+            if (__any_sync(FULL_MASK, any)) {
+                float v8[8];
+                v8[0] = -(q0.z * dx * s0 + q0.w * s1);     // d mu_x
+                v8[1] = -(q0.w * dx * s0 + q1.x * s1);     // d mu_y
+                v8[2] = -0.5f * dx * dx * s0;              // d A
+                v8[3] = -dx * s1;                          // d B (total)
+                v8[4] = -0.5f * s2;                        // d C
+                v8[5] = dr; v8[6] = dg; v8[7] = db;
+                const float tot = butterfly8(v8, lane);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) dop += __shfl_xor_sync(FULL_MASK, dop, o);
+                if (STAT) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) esq += __shfl_xor_sync(FULL_MASK, esq, o);
+                }
+                const int pid = __shfl_sync(FULL_MASK, id_this, kk);
+                int slotv = -1; float val = 0.f;
+                if ((lane & 3) == 0) { slotv = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); val = tot; }
+                else if (lane == 1) { slotv = 8; val = dop; }
+                else if (STAT && lane == 2) { slotv = 9; val = esq; }
+                if (slotv >= 0) atomicAdd(&grad[(size_t)pid * LGS_GRAD_FLOATS + slotv], val);   // RED.ADD.F32, result unused
+            }
+        }
+        __syncwarp();
+    }
+    st.drain();
+}
+
+// ---- unpack ----------------------------------------------------------------------------------------
+// 12-float accumulator -> the reference's SoA gradient tensors (GR/raster.cu:855-886), including the
+// de-normaliser of the max-normalised image gradient (wrapper.py:490-494).
+__global__ void unpack_kernel(const float* __restrict__ grad, const float* __restrict__ inv_scaler, int N, int H, int W,
+                              float* __restrict__ d_ndc, float* __restrict__ d_cov, float* __restrict__ d_color,
+                              float* __restrict__ d_opac, float* __restrict__ err_sum, float* __restrict__ err_sq)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (i >= N) return;
+    const float s = inv_scaler ? inv_scaler[0] : 1.0f;
+    const float4* g4 = reinterpret_cast<const float4*>(grad + ((size_t)b * N + i) * LGS_GRAD_FLOATS);
+    const float4 a = g4[0], c = g4[1], e = g4[2];
+    size_t o4 = (size_t)b * 4 * N + i, o3 = (size_t)b * 3 * N + i;
+    d_ndc[o4] = a.x * 0.5f * W * s; d_ndc[o4 + N] = a.y * 0.5f * H * s;
+    d_ndc[o4 + 2 * (size_t)N] = 0.f; d_ndc[o4 + 3 * (size_t)N] = 0.f;
+    d_cov[o4] = a.z * s; d_cov[o4 + N] = a.w * 0.5f * s; d_cov[o4 + 2 * (size_t)N] = a.w * 0.5f * s; d_cov[o4 + 3 * (size_t)N] = c.x * s;
+    d_color[o3] = c.y * s; d_color[o3 + N] = c.z * s; d_color[o3 + 2 * (size_t)N] = c.w * s;
+    if (b == 0) d_opac[i] = e.x * s;                      // view 0 only, as GR/raster.cu:881-884
+    if (err_sum) err_sum[(size_t)b * N + i] = 0.f;
+    if (err_sq) err_sq[(size_t)b * N + i] = e.y;
+}
+
+// ---- host entry points -----------------------------------------------------------------------------
+static int g_use_bulk = -1;
+static bool use_bulk()
+{
+    if (g_use_bulk < 0) {
+        const char* e = getenv("LGS_STAGING");     // "bulk" (default) | "cpasync"
+        g_use_bulk = (e && e[0] == 'c') ? 0 : 1;
+    }
+    return g_use_bulk == 1;
+}
+extern "C" int lgs_set_staging(int bulk) { g_use_bulk = bulk ? 1 : 0; return LGS_OK; }
+
+extern "C" int lgs_pack_params(const float* ndc, const float* cov2d_inv, const float* color, const float* opacity, int V, int N,
+                               int img_h, int img_w, float* packed_params, void* stream)
+{
+    if (N == 0) return LGS_OK;
+    pack_kernel<<<dim3(lgs_cdiv(N, 256), V), 256, 0, (cudaStream_t)stream>>>(ndc, cov2d_inv, color, opacity, (SplatRec*)packed_params, N,
+                                                                           img_h, img_w);
+    LGS_CHECK_LAUNCH("pack_kernel");
+    return LGS_OK;
+}
+
+// sorted_points i32[V,cap]; start_index i32[V,tiles+2]; packed f32[V,N,12]; specific_tiles i32[V,n_sel] or null.
+// img f32[V,3,Hp,Wp]; T f32[V,1,Hp,Wp]; last i16[V,1,Hp,Wp]; fragment_count i32[V,1,N] / weight f32[V,1,N]
+// (must be zero-initialised by the caller when enable_statistic).
+extern "C" int lgs_rasterize_forward_packed(const int* sorted_points, const int* start_index, const float* packed_params,
+                                            const int* specific_tiles, int n_specific, int V, int N, int cap, int img_h, int img_w,
+                                            int tile_h, int tile_w, int enable_statistic, float* img, float* transmittance,
+                                            short* last_contributor, int* fragment_count, float* fragment_weight, void* stream)
+{
+    LGS_REQUIRE(lgs_tile_ok(tile_h, tile_w), "rasterize_forward: tile %dx%d not one of 8x16, 12x16, 16x16, 8x8", tile_h, tile_w);
+    LGS_REQUIRE(V >= 1 && img_h > 0 && img_w > 0, "rasterize_forward: bad sizes V=%d H=%d W=%d", V, img_h, img_w);
+    int gx = (img_w + tile_w - 1) / tile_w, gy = (img_h + tile_h - 1) / tile_h;
+    int ntile = gx * gy, Hp = gy * tile_h, Wp = gx * tile_w;
+    int nrender = specific_tiles ? n_specific : ntile;
+    if (nrender == 0) return LGS_OK;
+    dim3 grid(lgs_cdiv(nrender, WARPS_PER_BLOCK), V), block(32, WARPS_PER_BLOCK);
+    cudaStream_t st = (cudaStream_t)stream;
+    const SplatRec* recs = (const SplatRec*)packed_params;
+    const bool bulk = use_bulk();
+#define FWD(S, B) raster_forward_kernel<TH, TW, S, B><<<grid, block, 0, st>>>(sorted_points, start_index, recs, specific_tiles, n_specific, \
+        img, transmittance, last_contributor, fragment_count, fragment_weight, gx, ntile, cap, N, Hp, Wp)
+    LGS_DISPATCH_TILE(tile_h, tile_w,
+        if (enable_statistic) { if (bulk) FWD(true, true); else FWD(true, false); }
+        else { if (bulk) FWD(false, true); else FWD(false, false); })
+#undef FWD
+    LGS_CHECK_LAUNCH("raster_forward_kernel");
+    return LGS_OK;
+}
+
+// packed_grad: f32[V,N,12] scratch, zeroed here.  d_trans may be null.  Outputs as GR/raster.cu:1021-1036.
+extern "C" int lgs_rasterize_backward(const int* sorted_points, const int* start_index, const float* packed_params,
+                                      const int* specific_tiles, int n_specific, const float* final_transmittance,
+                                      const short* last_contributor, const float* d_img, const float* d_trans_img,
+                                      const float* grad_inv_scaler, int V, int N, int cap, int img_h, int img_w, int tile_h,
+                                      int tile_w, int enable_statistic, float* packed_grad, float* d_ndc, float* d_cov2d_inv,
+                                      float* d_color, float* d_opacity, float* err_sum, float* err_square_sum, void* stream)
+{
+    LGS_REQUIRE(lgs_tile_ok(tile_h, tile_w), "rasterize_backward: tile %dx%d not one of 8x16, 12x16, 16x16, 8x8", tile_h, tile_w);
+    LGS_REQUIRE(V >= 1 && img_h > 0 && img_w > 0, "rasterize_backward: bad sizes V=%d H=%d W=%d", V, img_h, img_w);
+    int gx = (img_w + tile_w - 1) / tile_w, gy = (img_h + tile_h - 1) / tile_h;
+    int ntile = gx * gy, Hp = gy * tile_h, Wp = gx * tile_w;
+    int nrender = specific_tiles ? n_specific : ntile;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N == 0) return LGS_OK;
+    LGS_CUDA(cudaMemsetAsync(packed_grad, 0, sizeof(float) * (size_t)V * N * LGS_GRAD_FLOATS, st));
+    if (nrender > 0) {
+        dim3 grid(lgs_cdiv(nrender, WARPS_PER_BLOCK), V), block(32, WARPS_PER_BLOCK);
+        const SplatRec* recs = (const SplatRec*)packed_params;
+        const bool bulk = use_bulk();
+        const bool trans = d_trans_img != nullptr;
+#define BWD(S, T, B) raster_backward_kernel<TH, TW, S, T, B><<<grid, block, 0, st>>>(sorted_points, start_index, recs, specific_tiles, \
+        n_specific, final_transmittance, last_contributor, d_img, d_trans_img, packed_grad, gx, ntile, cap, N, Hp, Wp)
+        LGS_DISPATCH_TILE(tile_h, tile_w,
+            if (enable_statistic) { if (trans) { if (bulk) BWD(true, true, true); else BWD(true, true, false); }
+                                    else { if (bulk) BWD(true, false, true); else BWD(true, false, false); } }
+            else { if (trans) { if (bulk) BWD(false, true, true); else BWD(false, true, false); }
+                   else { if (bulk) BWD(false, false, true); else BWD(false, false, false); } })
+#undef BWD
+        LGS_CHECK_LAUNCH("raster_backward_kernel");
+    }
+    if (d_ndc != nullptr) {
+        unpack_kernel<<<dim3(lgs_cdiv(N, 256), V), 256, 0, st>>>(packed_grad, grad_inv_scaler, N, img_h, img_w, d_ndc, d_cov2d_inv, d_color,
+                                                                d_opacity, err_sum, err_square_sum);
+        LGS_CHECK_LAUNCH("unpack_kernel");
+    }
+    return LGS_OK;
+}
