@@ -170,6 +170,37 @@ int lgs_rasterize_backward(const int* sorted_points, const int* start_index, con
 /* staging selector for the raster kernels: 1 = cp.async.bulk + mbarrier (default), 0 = cp.async */
 int lgs_set_staging(int bulk);
 
+/* ---- fused per-view pipeline ("Level B") ---------------------------------------------------------------- */
+
+/* One kernel for the whole projection chain of one view: replaces cull_compact_activate + mvp_transform_forward +
+ * createTransformMatrix_forward + jacobianRayspace + createCov2dDirectly_forward + eigh_and_inv_2x2matrix_forward +
+ * get_allocate_size + pack_forward_params (render/__init__.py:26-61, wrapper.py:727-731, GR/raster.cu:334-356).
+ * A = number of allocated chunks (launch width; chunks >= *visible_chunks_num produce invisible records).
+ * Outputs over A*S compacted slots: packed_params f32[A*S,12] (slots 10,11 carry ndc.x, ndc.y for the emit pass),
+ * depth_key u32 (float bits of view z, 0xFFFFFFFF when invisible), iota u32 (slot index), tile_count i32,
+ * totals i32[1] = number of (tile,splat) pairs. */
+int lgs_project_forward(int sh_degree, const int64_t* visible_chunk_id, const int* visible_chunks_num,
+                        const float* view_matrix, const float* proj_matrix, const float* position, const float* scale,
+                        const float* rotation, const float* sh_base, const float* sh_rest, const float* opacity, int C,
+                        int S, int A, int img_h, int img_w, int tile_h, int tile_w, float* packed_params,
+                        unsigned* depth_key, unsigned* iota, int* tile_count, int* totals, void* stream);
+
+/* duplicate_with_keys (GR/binning.cu:33-110) reading the packed record: offset = inclusive scan of the depth-ordered
+ * counts, order = depth-sorted slot ids; keys/vals i32[cap] must be zero-initialised by the caller. */
+int lgs_emit_pairs(const float* packed_params, const int* offset, const unsigned* order, int n, int cap, int img_h,
+                   int img_w, int tile_h, int tile_w, int* keys, int* vals, void* stream);
+
+/* Record gradient (packed_grad f32[A*S,12] from lgs_rasterize_backward) -> the six compacted parameter gradients;
+ * replaces unpack_gradient + inv_2x2matrix_backward(+nan_to_num) + createCov2dDirectly_backward +
+ * createTransformMatrix_backward + mvp_transform_backward + activate_backward (wrapper.py:481-524,588-592,404-407,
+ * 190-193,278-285,820-845). */
+int lgs_project_backward(int sh_degree, const int64_t* visible_chunk_id, const int* visible_chunks_num,
+                         const float* view_matrix, const float* proj_matrix, const float* position, const float* scale,
+                         const float* rotation, const float* opacity, int C, int S, int A, int rest_dim, int img_h,
+                         int img_w, int true_sigmoid_grad, const float* packed_grad, const float* grad_inv_scaler,
+                         int zero_outputs, float* g_position, float* g_scale, float* g_rotation, float* g_sh_base,
+                         float* g_sh_rest, float* g_opacity, void* stream);
+
 /* ---- optimiser / statistics (next rows) ------------------------------------------------------ */
 
 /* adamUpdate, GR/compact.cu:320-417 (GR/compact.h:18-23): Adam WITHOUT bias correction. */

@@ -1,0 +1,163 @@
+"""The render operator: ``render_preprocess`` + ``render`` with the signatures of the reference's
+``litegs/render/__init__.py:11-94`` (Level A: op by op through ``litegs_b200.wrapper``), and
+``render_view`` -- the same computation as ONE differentiable call on the fused pipeline (Level B).
+
+Both levels produce the same image and the same six parameter gradients (tests/test_gpu_pipeline.py);
+Level B is what ``bench.py`` measures.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.cuda.nvtx as nvtx
+
+from . import fused as litegs_fused
+from . import pipeline, wrapper
+from .compacted import CompactedTensor
+from .statistics import StatisticsHelperInst
+
+
+def uncluster(*tensors):
+    """[..., chunks, chunk_size] -> [..., chunks*chunk_size] views (reference scene/cluster.py:24-28)."""
+    return tuple(t.reshape(*t.shape[:-2], t.shape[-2] * t.shape[-1]) for t in tensors)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Level A: the reference's two-call surface
+# ---------------------------------------------------------------------------------------------------
+
+def render_preprocess(cluster_origin, cluster_extend, frustumplane, view_matrix,
+                      xyz, scale, rot, sh_0, sh_rest, opacity,
+                      feedback_buffer, idx_tensor, pp, actived_sh_degree: int):
+    """Chunk frustum culling -> compaction -> activation (+ SH->RGB).
+
+    Returns (visible_chunkid, visible_chunks_num, culled_xyz [4,N], culled_scale [3,N], culled_rot [4,N],
+    color [V,3,N], culled_opacity [1,N]) exactly as render/__init__.py:11-48."""
+    visible_chunkid = None
+    visible_chunks_num = None
+    if pp.cluster_size:
+        if cluster_origin is None or cluster_extend is None:
+            raise RuntimeError("cluster_origin / cluster_extend are required when cluster_size > 0 "
+                               "(compute them with litegs_b200.scene.cluster_aabb or the caller's scene code)")
+        _, visible_chunks_num, visible_chunkid = litegs_fused.frustum_culling_aabb(cluster_origin, cluster_extend, frustumplane,
+                                                                                 feedback_buffer, idx_tensor)
+        if StatisticsHelperInst.bStart and StatisticsHelperInst.on_compact_mask is not None:
+            StatisticsHelperInst.on_compact_mask(visible_chunkid, visible_chunks_num)
+        culled = wrapper.CullCompactActivateWithSparseGrad.apply(pp.sparse_grad, actived_sh_degree, visible_chunkid,
+                                                                 visible_chunks_num, view_matrix, xyz, scale, rot, sh_0, sh_rest, opacity)
+        culled_xyz, culled_scale, culled_rot, color, culled_opacity = uncluster(*culled)
+    else:
+        nvtx.range_push("Activate")
+        ones = torch.ones((1, xyz.shape[-1]), dtype=xyz.dtype, device=xyz.device)
+        culled_xyz = torch.cat((xyz, ones), dim=0)
+        culled_scale = scale.exp()
+        culled_rot = torch.nn.functional.normalize(rot, dim=0)
+        culled_opacity = opacity.sigmoid()
+        with torch.no_grad():
+            R = view_matrix[..., :3, :3]
+            t = view_matrix[..., 3:4, :3]
+            camera_center = (-t @ R.transpose(-1, -2)).squeeze(1)
+            dirs = torch.nn.functional.normalize(culled_xyz[:3] - camera_center.unsqueeze(-1), dim=-2)
+        color = wrapper.SphericalHarmonicToRGB.call_fused(actived_sh_degree, sh_0, sh_rest, dirs)
+        nvtx.range_pop()
+    return visible_chunkid, visible_chunks_num, culled_xyz, culled_scale, culled_rot, color, culled_opacity
+
+
+def render(view_matrix, proj_matrix, xyz, scale, rot, color, opacity,
+           valid_length, feedback_binning_allocate_size, idx_tensor,
+           actived_sh_degree: int, output_shape, pp):
+    """Projection -> binning -> rasterisation; returns (img, transmittance, depth, normal, primitive_visible)
+    as render/__init__.py:50-94."""
+    nvtx.range_push("Proj")
+    view_pos, ndc_pos = wrapper.MVPTransform.apply(xyz, view_matrix, proj_matrix, valid_length)
+    transform_matrix = wrapper.CreateTransformMatrix.call_fused(scale, rot, valid_length)
+    J = wrapper.CreateRaySpaceTransformMatrix.call_fused(view_pos, proj_matrix, output_shape, valid_length)
+    cov2d = wrapper.CreateCov2dDirectly.call_fused(J, view_matrix, transform_matrix, valid_length)
+    _, _, inv_cov2d = wrapper.EighAndInverse2x2Matrix.call_fused(cov2d, valid_length)
+    view_depth = view_pos[:, 2, :]
+    nvtx.range_pop()
+
+    tile_start_index, sorted_pointId, primitive_visible = wrapper.Binning.call_fused(
+        ndc_pos, view_depth, inv_cov2d, opacity, valid_length, feedback_binning_allocate_size, idx_tensor,
+        output_shape, pp.tile_size)
+
+    tiles = None
+    cached = StatisticsHelperInst.cached_sorted_tile_list.get(StatisticsHelperInst.cur_sample)
+    if cached is not None:
+        tiles = cached.unsqueeze(0)
+    H, W = int(output_shape[0]), int(output_shape[1])
+    img, transmitance, depth, normal, last = wrapper.GaussiansRasterFunc.apply(
+        sorted_pointId, tile_start_index, ndc_pos, inv_cov2d, color, opacity, tiles, H, W,
+        pp.tile_size[0], pp.tile_size[1], pp.enable_transmitance, pp.enable_depth)
+    if StatisticsHelperInst.bStart and StatisticsHelperInst.on_blend_count is not None:
+        StatisticsHelperInst.on_blend_count(last, pp.tile_size[0], pp.tile_size[1])
+
+    img = img[..., :H, :W].clamp(0, 1).contiguous()
+    if transmitance is not None:
+        transmitance = transmitance[..., :H, :W].contiguous()
+    if depth is not None:
+        depth = depth[..., :H, :W].contiguous()
+    return img, transmitance, depth, normal, primitive_visible
+
+
+# ---------------------------------------------------------------------------------------------------
+# Level B: one differentiable call per view
+# ---------------------------------------------------------------------------------------------------
+
+class _RenderViewFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz, scale, rot, sh_0, sh_rest, opacity, cluster_origin, cluster_extend, frustumplane,
+                view_matrix, proj_matrix, sh_degree, H, W, th, tw, sparse_grad, enable_transmitance):
+        params = dict(xyz=xyz, scale=scale, rot=rot, sh_0=sh_0, sh_rest=sh_rest, opacity=opacity)
+        stat = bool(StatisticsHelperInst.bStart)
+        img, state, stats = pipeline.render_view_forward(params, cluster_origin, cluster_extend, frustumplane, view_matrix,
+                                                         proj_matrix, sh_degree, (H, W), (th, tw), enable_statistic=stat)
+        ctx.state = state
+        ctx.stats = stats
+        ctx.stat = stat
+        ctx.sparse = bool(sparse_grad)
+        ctx.trans = bool(enable_transmitance)
+        ctx.save_for_backward(xyz, scale, rot, sh_0, sh_rest, opacity)
+        ctx.mark_non_differentiable(state.last)
+        return img, state.T, state.last
+
+    @staticmethod
+    def backward(ctx, g_img, g_T, _g_last):
+        xyz, scale, rot, sh_0, sh_rest, opacity = ctx.saved_tensors
+        params = dict(xyz=xyz, scale=scale, rot=rot, sh_0=sh_0, sh_rest=sh_rest, opacity=opacity)
+        state = ctx.state
+        if g_img is None:
+            g_img = torch.zeros((1, 3, *state.T.shape[-2:]), dtype=torch.float32, device=xyz.device)
+        grads, pg = pipeline.render_view_backward(params, state, g_img, g_T if ctx.trans else None, enable_statistic=ctx.stat)
+        if ctx.stat and StatisticsHelperInst.on_fragment_weight is not None:
+            StatisticsHelperInst.on_fragment_weight(ctx.stats[1], ctx.stats[0])
+        C, S = xyz.shape[-2:]
+        ids = state.chunk_ids[: state.n_chunks_visible]
+        out = []
+        for g in grads:
+            ct = CompactedTensor((*g.shape[:-2], C, S), ids, g)
+            out.append(ct if ctx.sparse else ct.to_dense())
+        ctx.state = None
+        return (*out, None, None, None, None, None, None, None, None, None, None, None, None)
+
+
+def render_view(cluster_origin, cluster_extend, frustumplane, view_matrix, proj_matrix,
+                xyz, scale, rot, sh_0, sh_rest, opacity, actived_sh_degree: int, output_shape, pp):
+    """render_preprocess + render of one view on the fused pipeline.
+
+    Same inputs as the two reference calls (raw clustered parameters, chunk AABBs, camera); returns
+    (img [1,3,H,W] clamped to [0,1], transmittance or None, depth=None, normal=None, visible_chunkid,
+    visible_chunks_num).  Gradients reach the six parameter tensors as CompactedTensor (pp.sparse_grad)
+    or dense tensors."""
+    if not pp.cluster_size:
+        raise RuntimeError("render_view needs the clustered layout (cluster_size > 0); use render_preprocess + render otherwise")
+    H, W = int(output_shape[0]), int(output_shape[1])
+    th, tw = int(pp.tile_size[0]), int(pp.tile_size[1])
+    img, T, last = _RenderViewFn.apply(xyz, scale, rot, sh_0, sh_rest, opacity, cluster_origin, cluster_extend, frustumplane,
+                                       view_matrix, proj_matrix, int(actived_sh_degree), H, W, th, tw, pp.sparse_grad,
+                                       pp.enable_transmitance)
+    img = img[..., :H, :W].clamp(0, 1)
+    trans = T[..., :H, :W] if pp.enable_transmitance else None
+    return img, trans, None, None, last

@@ -1,0 +1,75 @@
+"""Recipe that compiles the UNMODIFIED reference extension (litegs/submodules/gaussian_raster) for sm_100a.
+
+TEST INFRASTRUCTURE ONLY.  Sources are compiled where they lie under /root/reference (nothing is
+copied into this repository); the only output is ``oracle/_ref/litegs_fused_ref.so`` (git-ignored,
+NOT gpurun-ignored, so it travels to the GPU box).  It is the "reference itself run here" that pins the
+CPU oracle (tests/test_gpu_vs_reference.py, tests/golden/make_golden.py) and the CUDA baseline that
+``bench.py`` times next to ours ("ref_cuda").  Flags are the reference's own: -O3 --use_fast_math
+(GR/setup.py:33-36) plus the arch.  The reference's build system (setup.py / CMake) is not run.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "_ref")
+REF_GR = "/root/reference/litegs/submodules/gaussian_raster"
+NAME = "litegs_fused_ref"
+SOURCES = ["binning.cu", "compact.cu", "cuda_errchk.cpp", "ext_cuda.cpp", "raster.cu", "transform.cu"]
+
+
+def so_path():
+    if not os.path.isdir(OUT):
+        return None
+    for f in os.listdir(OUT):
+        if f.startswith(NAME) and f.endswith(".so"):
+            return os.path.join(OUT, f)
+    return None
+
+
+def build(quiet: bool = False):
+    """Build oracle/_ref/litegs_fused_ref.so if the reference tree is present; returns the path or None."""
+    if so_path() is not None:
+        return so_path()
+    if not os.path.isdir(REF_GR):
+        if not quiet:
+            print("[build_ref] /root/reference not present: nothing to build")
+        return None
+    os.makedirs(OUT, exist_ok=True)
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
+    os.environ["CXX"] = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else os.environ.get("CXX", "g++")
+    os.environ["CC"] = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else os.environ.get("CC", "gcc")
+    from torch.utils import cpp_extension
+    # the reference's own setup.py strips torch's "no half operators" defines (GR/setup.py:4-16)
+    for flag in ("-D__CUDA_NO_HALF_OPERATORS__", "-D__CUDA_NO_HALF_CONVERSIONS__", "-D__CUDA_NO_BFLOAT16_CONVERSIONS__",
+                 "-D__CUDA_NO_HALF2_OPERATORS__"):
+        if flag in cpp_extension.COMMON_NVCC_FLAGS:
+            cpp_extension.COMMON_NVCC_FLAGS.remove(flag)
+    cpp_extension.load(
+        name=NAME,
+        sources=[os.path.join(REF_GR, s) for s in SOURCES],
+        extra_cflags=["-O3"],
+        extra_cuda_cflags=["-O3", "--use_fast_math", "-gencode", "arch=compute_100a,code=sm_100a"],
+        build_directory=OUT,
+        verbose=not quiet,
+        is_python_module=True,
+    )
+    return so_path()
+
+
+def load():
+    """Import the prebuilt reference module (needs torch; used on the GPU box). Returns None if absent."""
+    p = so_path()
+    if p is None:
+        return None
+    import torch  # noqa: F401  (registers the ATen symbols the extension links against)
+    spec = importlib.util.spec_from_file_location(NAME, p)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+if __name__ == "__main__":
+    print(build(quiet="-q" in sys.argv))
