@@ -1,0 +1,511 @@
+#!/usr/bin/env python
+"""bench.py -- forward+backward views/s of the render hot path on the BASELINE.json workload.
+
+    python bench.py --gpus 1 --steps K --warmup W                 (ours, N=1)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W                    (ours, N GPUs of one node, NCCL)
+    python bench.py --impl reference ...                          (the CPU restatement of the reference path)
+
+Workload (BASELINE.json configs[1], BASELINE.md "Synthetic inputs"): 1M random Gaussians (seed 0), 1920x1080,
+sh_degree 3, cameras on the radius-3 Fibonacci sphere.  A step = `views_per_rank` views per rank, each one
+render_view forward + ``(img*w).sum()`` backward down to the six parameter gradients, accumulated into the
+dense per-Gaussian gradient buffer; with N>1 ranks the buffer is all-reduced once per step (weak scaling:
+per-GPU work fixed).  `value` = views of all ranks / max-over-ranks device time, inputs resident in HBM.
+`e2e` = same through the public API with the per-view host inputs (camera matrices + uint8 target image in
+pinned memory) copied H2D and the loss read back D2H inside the timed region.
+
+Inputs are larger than L2 (236 MB of parameters are streamed by every view), so no explicit L2 flush is needed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "forward+backward views/sec @1080p 1M Gaussians"
+UNIT = "views/s"
+PARAM_KEYS = ("xyz", "scale", "rot", "sh_0", "sh_rest", "opacity")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gaussians", type=int, default=1_000_000)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--tile", default="16x16", help="8x16 (reference default) | 12x16 | 16x16 | 8x8")
+    ap.add_argument("--sh-degree", type=int, default=3)
+    ap.add_argument("--views-per-rank", type=int, default=8)
+    ap.add_argument("--n-views", type=int, default=64, help="size of the camera lattice the step's views are drawn from")
+    ap.add_argument("--cpu-views", type=int, default=2, help="views of the CPU baseline sample (N=1 only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--level", default="B", choices=["A", "B"], help="B = fused render_view (default), A = op-by-op surface")
+    ap.add_argument("--staging", default=None, choices=[None, "bulk", "cpasync"])
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile(prefix="clocks_", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            sm, mx, reasons = [], [], set()
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1])); mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            if sm:
+                out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return out
+
+
+class StageTimer:
+    """CUDA events around each C-ABI call (on the stream the kernels are launched on), to attribute the step
+    time to stages and to give the roofline its per-launch duration."""
+
+    def __init__(self):
+        self.enabled = False
+        self.rec = {}
+
+    def install(self):
+        import torch
+        from litegs_b200 import _lib
+        orig = _lib.call
+        timer = self
+
+        def call(name, *a):
+            if not timer.enabled:
+                return orig(name, *a)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            orig(name, *a)
+            e1.record()
+            timer.rec.setdefault(name, []).append((e0, e1))
+        _lib.call = call
+
+    def summary(self):
+        """name -> (total ms, launches)."""
+        out = {}
+        for name, evs in self.rec.items():
+            out[name] = (sum(a.elapsed_time(b) for a, b in evs), len(evs))
+        return out
+
+
+def load_scene(args):
+    from litegs_b200 import scene
+    return scene.make_scene(args.gaussians, sh_degree=3, seed=0)
+
+
+def camera_np(i, args):
+    from litegs_b200 import scene
+    return scene.make_camera(i % args.n_views, args.n_views, args.width, args.height)
+
+
+def stage_bytes(stats, S, K):
+    """Algorithmic bytes per view and stage."""
+    Nv, Nmax, D, P, Nvis = stats["Nv"], stats["Nmax"], stats["D"], stats["P"], stats["N_visible"]
+    par = 4 * (3 + 3 + 4 + 3 * K + 1)
+    bits_passes = stats["tile_sort_passes"]
+    return {
+        "lgs_frustum_culling_aabb": 28 * (Nmax // S),
+        "lgs_project_forward": par * Nv + 60 * Nmax,
+        "lgs_sort_pairs_u32(depth)": (4 + 4 * 16) * Nv,
+        "lgs_scan_gathered": 12 * Nv,
+        "lgs_emit_pairs": 60 * Nv + 8 * D,
+        "lgs_sort_pairs_u32(tile)": (4 + bits_passes * 16) * D,
+        "lgs_tile_range": 4 * D,
+        "lgs_rasterize_forward_packed": 4 * D + 48 * Nvis + 18 * P,
+        "lgs_rasterize_backward": 48 * Nmax + 4 * D + 48 * Nvis + 30 * P + 36 * Nvis,
+        "lgs_project_backward": 48 * Nv + 44 * Nv + par * Nv,
+        "lgs_sparse_chunk_op": 3 * par * Nv,
+    }
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm (oracle): used for cpu_baseline inside the "ours" line and as the whole `--impl reference` run
+# ---------------------------------------------------------------------------------------------------
+
+def cpu_views_per_s(args, scene_np, n_views, weights_seed=1):
+    import oracle
+    P = {k: scene_np[k] for k in PARAM_KEYS}
+    aabb = (scene_np["cluster_origin"], scene_np["cluster_extend"])
+    th, tw = [int(x) for x in args.tile.split("x")]
+    H, W = args.height, args.width
+    w = np.random.default_rng(weights_seed).standard_normal((1, 3, H, W), dtype=np.float32)
+    t0 = time.perf_counter()
+    for i in range(n_views):
+        cam = camera_np(i, args)
+        oracle.render_forward_backward(P, aabb, cam, (H, W), (th, tw), args.sh_degree, lambda img: w)
+    dt = time.perf_counter() - t0
+    return n_views / dt, dt, oracle.num_threads()
+
+
+def run_reference(args, rank):
+    """The reference has no CPU implementation of this path; its CPU arm is the oracle port
+    (oracle/, C + OpenMP on all host threads), one full-size view per step."""
+    if rank != 0:
+        return
+    scene_np = load_scene(args)
+    import oracle
+    for _ in range(min(args.warmup, 1)):
+        cpu_views_per_s(args, scene_np, 1)
+    t0 = time.perf_counter()
+    vps, dt, threads = cpu_views_per_s(args, scene_np, max(1, args.steps))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": vps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * dt / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.gaussians} Gaussians, {args.width}x{args.height}, sh_degree {args.sh_degree}, tile {args.tile}",
+                   "views_per_step": 1},
+        "cpu_baseline": {"value": vps, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{max(1, args.steps)} full-size views, one per step (oracle/, C + OpenMP)"},
+        "e2e": {"value": vps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    # informational: the reference's own CUDA kernels (sm_100a build in oracle/_ref) under the same op-level
+    # orchestration, when a GPU and the prebuilt module are available.
+    try:
+        line["ref_cuda"] = ref_cuda_views_per_s(args, scene_np)
+    except Exception as e:  # pragma: no cover
+        line["ref_cuda"] = {"unavailable": str(e)[:200]}
+    print(json.dumps(line), flush=True)
+
+
+def ref_cuda_views_per_s(args, scene_np, iters=20):
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("no GPU")
+    from oracle import build_ref
+    mod = build_ref.load()
+    if mod is None:
+        raise RuntimeError("oracle/_ref not built")
+    from litegs_b200 import render, wrapper
+    from litegs_b200.arguments import PipelineParams
+    dev = torch.device("cuda:0")
+    th, tw = [int(x) for x in args.tile.split("x")]
+    pp = PipelineParams(tile_size=(th, tw))
+    out = {}
+    for name, backend in (("reference_kernels", mod), ("ours_level_a", None)):
+        wrapper.set_backend(backend if backend is not None else __import__("litegs_b200.fused", fromlist=["x"]))
+        try:
+            P = {k: torch.from_numpy(scene_np[k]).to(dev).requires_grad_(True) for k in PARAM_KEYS}
+            A = [torch.from_numpy(scene_np[k]).to(dev) for k in ("cluster_origin", "cluster_extend")]
+            w = torch.randn((1, 3, args.height, args.width), device=dev)
+            cams = [{k: torch.from_numpy(v).to(dev) for k, v in camera_np(i, args).items()} for i in range(8)]
+
+            def one(i):
+                c = cams[i % 8]
+                ids, num, cx, cs, cr, col, cop = render.render_preprocess(A[0], A[1], c["frustumplane"], c["view"], P["xyz"], P["scale"],
+                                                                          P["rot"], P["sh_0"], P["sh_rest"], P["opacity"], None, None, pp,
+                                                                          args.sh_degree)
+                img = render.render(c["view"], c["proj"], cx, cs, cr, col, cop, num * pp.cluster_size, None, None, args.sh_degree,
+                                    (args.height, args.width), pp)[0]
+                (img * w).sum().backward()
+                for k in PARAM_KEYS:
+                    P[k].grad = None
+            for i in range(3):
+                one(i)
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(iters):
+                one(i)
+            e1.record(); torch.cuda.synchronize()
+            out[name] = {"value": iters / (e0.elapsed_time(e1) / 1000.0), "unit": UNIT}
+        finally:
+            wrapper.set_backend(__import__("litegs_b200.fused", fromlist=["x"]))
+    out["note"] = "same Python orchestration (litegs_b200.render Level A) on the reference's kernels (fp16 blend) vs ours (fp32)"
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# ours
+# ---------------------------------------------------------------------------------------------------
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from litegs_b200 import _lib, dist as lgs_dist, pipeline, render
+    from litegs_b200.arguments import PipelineParams
+
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    _lib.load()
+    if args.staging:
+        _lib.call("lgs_set_staging", 1 if args.staging == "bulk" else 0)
+    th, tw = [int(x) for x in args.tile.split("x")]
+    H, W = args.height, args.width
+    pp = PipelineParams(tile_size=(th, tw), sparse_grad=True)
+
+    scene_np = load_scene(args)
+    P = {k: torch.from_numpy(scene_np[k]).to(dev).requires_grad_(True) for k in PARAM_KEYS}
+    A = [torch.from_numpy(scene_np[k]).to(dev) for k in ("cluster_origin", "cluster_extend")]
+    C_chunks, S = P["xyz"].shape[-2:]
+    K = (args.sh_degree + 1) ** 2
+    vpr = args.views_per_rank
+    my_views = [rank + world * j for j in range(vpr)]
+    cams_np = [camera_np(v, args) for v in my_views]
+    cams = [{k: torch.from_numpy(v).to(dev) for k, v in c.items()} for c in cams_np]
+    g = torch.Generator(device="cpu").manual_seed(1)
+    w_host = torch.randn((1, 3, H, W), generator=g)
+    w = w_host.to(dev)
+    acc = lgs_dist.GradAccumulator(P)
+    timer = StageTimer(); timer.install()
+    launches = {"n": 0}
+
+    def render_one(cam, weight):
+        if args.level == "B":
+            img = render.render_view(A[0], A[1], cam["frustumplane"], cam["view"], cam["proj"], P["xyz"], P["scale"], P["rot"],
+                                     P["sh_0"], P["sh_rest"], P["opacity"], args.sh_degree, (H, W), pp)[0]
+        else:
+            ids, num, cx, cs, cr, col, cop = render.render_preprocess(A[0], A[1], cam["frustumplane"], cam["view"], P["xyz"], P["scale"],
+                                                                      P["rot"], P["sh_0"], P["sh_rest"], P["opacity"], None, None, pp,
+                                                                      args.sh_degree)
+            img = render.render(cam["view"], cam["proj"], cx, cs, cr, col, cop, num * pp.cluster_size, None, None, args.sh_degree,
+                                (H, W), pp)[0]
+        loss = (img * weight).sum()
+        loss.backward()
+        g0 = P["xyz"].grad
+        ids = g0.chunk_ids
+        cnt = torch.tensor([ids.shape[0]], dtype=torch.int32, device=dev) if args.level == "A" else None
+        if cnt is None:
+            cnt = torch.full((1,), ids.shape[0], dtype=torch.int32, device=dev)
+        acc.add_view({k: P[k].grad.compacted_values for k in PARAM_KEYS}, ids, cnt)
+        for k in PARAM_KEYS:
+            P[k].grad = None
+        return loss
+
+    def step():
+        acc.zero_()
+        for c in cams:
+            render_one(c, w)
+        if world > 1:
+            acc.all_reduce()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- value: inputs resident ------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    timer.enabled = True
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    timer.enabled = False
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    total_views = vpr * world * args.steps
+    value = total_views / (ms / 1000.0)
+
+    # per-view workload statistics (for the roofline arithmetic), from one extra un-timed view
+    with torch.no_grad():
+        params = {k: P[k].detach() for k in PARAM_KEYS}
+        _, st, _ = pipeline.render_view_forward(params, A[0], A[1], cams[0]["frustumplane"], cams[0]["view"], cams[0]["proj"],
+                                                args.sh_degree, (H, W), (th, tw))
+        gx, gy = (W + tw - 1) // tw, (H + th - 1) // th
+        stats = {"Nv": st.n_chunks_visible * S, "Nmax": C_chunks * S, "D": st.n_pairs, "P": gx * tw * gy * th,
+                 "N_visible": int((st.tile_count[: st.n_chunks_visible * S] > 0).sum().item()),
+                 "tiles": gx * gy, "tile_sort_passes": math.ceil((gx * gy).bit_length() / 8),
+                 "mean_contributors_per_pixel": float(st.last.float().mean().item()),
+                 "max_list_len": int((st.ranges[0, 1:] - st.ranges[0, :-1]).clamp_min(0).max().item())}
+
+    # ---- e2e: host inputs, H2D + D2H inside the timed region ------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        gt_host = [(torch.rand((1, 3, H, W), generator=g) * 255).to(torch.uint8).pin_memory() for _ in range(2)]
+        cam_host = [{k: torch.from_numpy(v).pin_memory() for k, v in c.items()} for c in cams_np]
+        h2d = sum(v.numel() * v.element_size() for v in cam_host[0].values()) + gt_host[0].numel()
+        losses = []
+
+        def e2e_step():
+            acc.zero_()
+            for j in range(vpr):
+                cam = {k: v.to(dev, non_blocking=True) for k, v in cam_host[j].items()}
+                gt = gt_host[j % 2].to(dev, non_blocking=True)
+                weight = gt.float() * (1.0 / 255.0) - 0.5
+                loss = render_one(cam, weight)
+                losses.append(float(loss.item()))        # D2H read of the step's result
+            if world > 1:
+                acc.all_reduce()
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
+        n_e2e = max(1, args.steps // 2)
+        f0.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        f1.record()
+        barrier()
+        t2 = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e = {"value": vpr * world * n_e2e / (float(t2.item()) / 1000.0), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d * vpr), "d2h_bytes_per_step": int(4 * vpr)}
+
+    if rank != 0:
+        return
+    # ---- stage attribution + roofline -------------------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    summ = timer.summary()
+    n_views_rank = vpr * args.steps
+    bytes_per = stage_bytes(stats, S, K)
+    stages = {}
+    sort_calls = summ.get("lgs_sort_pairs_u32")
+    for name, (tot, n) in summ.items():
+        stages[name] = {"ms_per_view": tot / n_views_rank, "launches_per_view": n / n_views_rank}
+    # the two radix sorts share an entry point: split by call parity (depth sort first, tile sort second)
+    if "lgs_sort_pairs_u32" in timer.rec:
+        evs = timer.rec["lgs_sort_pairs_u32"]
+        d = sum(a.elapsed_time(b) for a, b in evs[0::2]) / n_views_rank
+        tl = sum(a.elapsed_time(b) for a, b in evs[1::2]) / n_views_rank
+        stages["lgs_sort_pairs_u32(depth)"] = {"ms_per_view": d, "launches_per_view": 1.0}
+        stages["lgs_sort_pairs_u32(tile)"] = {"ms_per_view": tl, "launches_per_view": 1.0}
+        del stages["lgs_sort_pairs_u32"]
+    for name, s_ in stages.items():
+        b = bytes_per.get(name)
+        if b is not None and s_["ms_per_view"] > 0:
+            s_["alg_bytes"] = int(b)
+            s_["gbs"] = b / (s_["ms_per_view"] / 1000.0) / 1e9
+    dom = max(stages.items(), key=lambda kv: kv[1]["ms_per_view"])[0] if stages else None
+    roofline = None
+    if dom is not None and "gbs" in stages[dom]:
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": stages[dom]["gbs"], "peak": peak_gbs, "unit": "GB/s",
+                    "frac": stages[dom]["gbs"] / peak_gbs, "traffic": None, "peak_source": peak_src,
+                    "alg_bytes_per_launch": stages[dom]["alg_bytes"], "ms_per_launch": stages[dom]["ms_per_view"]}
+    path_bytes = sum(v for k, v in bytes_per.items())
+    survey_bytes = 748 * stats["Nv"] + 172 * stats["D"] + 48 * stats["P"]
+    ms_view = ms / (vpr * args.steps)
+    path = {"alg_bytes_per_view": int(path_bytes), "gbs": path_bytes / (ms_view / 1000.0) / 1e9,
+            "frac": path_bytes / (ms_view / 1000.0) / 1e9 / peak_gbs,
+            "survey_formula_bytes": int(survey_bytes), "survey_formula_frac": survey_bytes / (ms_view / 1000.0) / 1e9 / peak_gbs,
+            "ms_per_view": ms_view}
+    hand_written = ("lgs_frustum_culling_aabb", "lgs_project_forward", "lgs_emit_pairs", "lgs_tile_range", "lgs_rasterize_forward_packed",
+                    "lgs_rasterize_backward", "lgs_project_backward", "lgs_sparse_chunk_op", "lgs_pack_params")
+    gpu_launches = 0
+    for name, (tot, n) in summ.items():
+        if name in hand_written:
+            mult = {"lgs_tile_range": 2}.get(name, 1)       # fill + range kernels
+            gpu_launches += n * mult
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{args.gaussians} Gaussians (seed 0), {W}x{H}, sh_degree {args.sh_degree}, tile {args.tile}, "
+                               f"{vpr} views/rank/step + dense grad accumulate" + (" + NCCL all-reduce" if world > 1 else ""),
+                   "parallelism": f"dp{world} (views sharded, parameters replicated)", "level": args.level,
+                   "l2": "inputs exceed L2 (236 MB of parameters streamed per view); no explicit flush",
+                   "staging": args.staging or os.environ.get("LGS_STAGING", "bulk")},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches),
+        "roofline": roofline, "path_roofline": path, "workload_stats": stats, "stages": stages,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            vps, dt, threads = cpu_views_per_s(args, scene_np, args.cpu_views)
+            line["cpu_baseline"] = {"value": vps, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{args.cpu_views} full-size views of the same workload (oracle/, C + OpenMP), {dt:.1f} s"}
+        except Exception as e:
+            line["cpu_baseline"] = {"unavailable": str(e)[:200]}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if args.gpus > 1 and world == 1:
+        sys.exit("bench.py --gpus N>1 must be launched with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N "
+                 "--master-addr 127.0.0.1 --master-port P bench.py --gpus N ...")
+    import torch
+    if not torch.cuda.is_available():
+        sys.exit("bench.py needs a CUDA device: litegs_b200 has no CPU path")
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -13,7 +13,6 @@ from typing import Optional
 import torch
 import torch.cuda.nvtx as nvtx
 
-from . import fused as litegs_fused
 from . import pipeline, wrapper
 from .compacted import CompactedTensor
 from .statistics import StatisticsHelperInst
@@ -41,7 +40,7 @@ def render_preprocess(cluster_origin, cluster_extend, frustumplane, view_matrix,
         if cluster_origin is None or cluster_extend is None:
             raise RuntimeError("cluster_origin / cluster_extend are required when cluster_size > 0 "
                                "(compute them with litegs_b200.scene.cluster_aabb or the caller's scene code)")
-        _, visible_chunks_num, visible_chunkid = litegs_fused.frustum_culling_aabb(cluster_origin, cluster_extend, frustumplane,
+        _, visible_chunks_num, visible_chunkid = wrapper.litegs_fused.frustum_culling_aabb(cluster_origin, cluster_extend, frustumplane,
                                                                                  feedback_buffer, idx_tensor)
         if StatisticsHelperInst.bStart and StatisticsHelperInst.on_compact_mask is not None:
             StatisticsHelperInst.on_compact_mask(visible_chunkid, visible_chunks_num)

@@ -18,6 +18,14 @@ from .compacted import CompactedTensor
 from .statistics import StatisticsHelperInst
 
 
+def set_backend(module) -> None:
+    """Route every operator of this module (and render.render_preprocess / render) to another object with the
+    ``litegs_fused`` surface.  Used by tests and bench.py to run the SAME orchestration on the reference's own
+    kernels (oracle/_ref) for the Tier-2 comparison; the default is ``litegs_b200.fused``."""
+    global litegs_fused
+    litegs_fused = module
+
+
 class _Op:
     """call_fused / call, as on the reference's BaseWrapper (wrapper.py:149-159)."""
     @classmethod
