@@ -304,10 +304,16 @@ def run_ours(args, rank, world, local_rank):
     timer = StageTimer(); timer.install()
     launches = {"n": 0}
 
+    acc_views = acc.grads()
+
     def render_one(cam, weight):
         if args.level == "B":
+            # fused path: the backward kernel adds this view's gradients straight into the dense buffer
             img = render.render_view(A[0], A[1], cam["frustumplane"], cam["view"], cam["proj"], P["xyz"], P["scale"], P["rot"],
-                                     P["sh_0"], P["sh_rest"], P["opacity"], args.sh_degree, (H, W), pp)[0]
+                                     P["sh_0"], P["sh_rest"], P["opacity"], args.sh_degree, (H, W), pp, accumulate_into=acc_views)[0]
+            loss = (img * weight).sum()
+            loss.backward()
+            return loss
         else:
             ids, num, cx, cs, cr, col, cop = render.render_preprocess(A[0], A[1], cam["frustumplane"], cam["view"], P["xyz"], P["scale"],
                                                                       P["rot"], P["sh_0"], P["sh_rest"], P["opacity"], None, None, pp,

@@ -169,6 +169,8 @@ int lgs_rasterize_backward(const int* sorted_points, const int* start_index, con
 
 /* staging selector for the raster kernels: 1 = cp.async.bulk + mbarrier (default), 0 = cp.async */
 int lgs_set_staging(int bulk);
+/* tiles (warps) per CTA of the raster kernels: 1, 2 or 4 (default 4, env LGS_WPB) */
+int lgs_set_warps_per_block(int wpb);
 
 /* ---- fused per-view pipeline ("Level B") ---------------------------------------------------------------- */
 
@@ -193,7 +195,8 @@ int lgs_emit_pairs(const float* packed_params, const int* offset, const unsigned
 /* Record gradient (packed_grad f32[A*S,12] from lgs_rasterize_backward) -> the six compacted parameter gradients;
  * replaces unpack_gradient + inv_2x2matrix_backward(+nan_to_num) + createCov2dDirectly_backward +
  * createTransformMatrix_backward + mvp_transform_backward + activate_backward (wrapper.py:481-524,588-592,404-407,
- * 190-193,278-285,820-845). */
+ * 190-193,278-285,820-845).  zero_outputs: 0 = assign compacted [..,A,S] outputs, 1 = clear them first,
+ * 2 = ACCUMULATE into dense [..,C,S] gradient tensors at the source chunk (multi-view / data-parallel path). */
 int lgs_project_backward(int sh_degree, const int64_t* visible_chunk_id, const int* visible_chunks_num,
                          const float* view_matrix, const float* proj_matrix, const float* position, const float* scale,
                          const float* rotation, const float* opacity, int C, int S, int A, int rest_dim, int img_h,

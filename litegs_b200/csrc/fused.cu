@@ -222,7 +222,7 @@ __global__ void project_backward_kernel(
     const int64_t* __restrict__ chunk_ids, const int* __restrict__ visible_num, const float* __restrict__ view,
     const float* __restrict__ proj, const float* __restrict__ pos, const float* __restrict__ scale,
     const float* __restrict__ rot, const float* __restrict__ opac, int C, int S, int A, int rest_dim, int H, int W,
-    int true_sigmoid, const float* __restrict__ grad /*[A*S,12]*/, const float* __restrict__ inv_scaler,
+    int true_sigmoid, int accumulate, const float* __restrict__ grad /*[A*S,12]*/, const float* __restrict__ inv_scaler,
     float* __restrict__ g_pos, float* __restrict__ g_scale, float* __restrict__ g_rot, float* __restrict__ g_sh0,
     float* __restrict__ g_shr, float* __restrict__ g_opac)
 {
@@ -307,6 +307,27 @@ __global__ void project_backward_kernel(
 #pragma unroll
             for (int k = 0; k < K; k++) o_sh[c][k] = b[k] * dcol[c];
     }
+    if (accumulate) {
+        // dense accumulation: outputs are the full [..,C,S] gradient tensors, this view's contribution is added at
+        // the SOURCE chunk (each Gaussian is owned by exactly one thread of one launch: no atomics needed);
+        // Gaussians that received no gradient are not touched at all.
+        if (any) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) g_pos[k * CS + src] += o_pos[k];
+#pragma unroll
+            for (int k = 0; k < 3; k++) g_scale[k * CS + src] += o_sc[k];
+#pragma unroll
+            for (int k = 0; k < 4; k++) g_rot[k * CS + src] += o_q[k];
+            g_opac[src] += o_op;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                g_sh0[c * CS + src] += o_sh[c][0];
+#pragma unroll
+                for (int k = 1; k < K; k++) g_shr[((size_t)(k - 1) * 3 + c) * CS + src] += o_sh[c][k];
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < 3; k++) g_pos[k * AS + dst] = o_pos[k];
 #pragma unroll
@@ -323,8 +344,9 @@ __global__ void project_backward_kernel(
     (void)rest_dim;
 }
 
-// zero_outputs=1 clears every output first (rows of chunks >= *visible_num and sh_rest rows above the active
-// degree must read as zero); a caller that hands in zero-initialised buffers can pass 0.
+// mode 0: outputs are compacted [..,A,S] and assigned; mode 1: same, cleared first (rows of chunks >= *visible_num and
+// sh_rest rows above the active degree must read as zero); mode 2: outputs are the DENSE [..,C,S] gradient tensors and
+// this view's gradients are accumulated into them (the multi-view / data-parallel path: no compacted round trip).
 extern "C" int lgs_project_backward(int sh_degree, const int64_t* visible_chunk_id, const int* visible_chunks_num,
                                     const float* view_matrix, const float* proj_matrix, const float* position,
                                     const float* scale, const float* rotation, const float* opacity, int C, int S, int A,
@@ -339,7 +361,8 @@ extern "C" int lgs_project_backward(int sh_degree, const int64_t* visible_chunk_
     if (A == 0) return LGS_OK;
     cudaStream_t st = (cudaStream_t)stream;
     size_t AS = (size_t)A * S;
-    if (zero_outputs) {
+    const int accumulate = (zero_outputs == 2) ? 1 : 0;
+    if (zero_outputs == 1) {
         LGS_CUDA(cudaMemsetAsync(g_position, 0, sizeof(float) * 3 * AS, st));
         LGS_CUDA(cudaMemsetAsync(g_scale, 0, sizeof(float) * 3 * AS, st));
         LGS_CUDA(cudaMemsetAsync(g_rotation, 0, sizeof(float) * 4 * AS, st));
@@ -348,7 +371,7 @@ extern "C" int lgs_project_backward(int sh_degree, const int64_t* visible_chunk_
         LGS_CUDA(cudaMemsetAsync(g_opacity, 0, sizeof(float) * AS, st));
     }
 #define PB(D) project_backward_kernel<D><<<A, S, 0, st>>>(visible_chunk_id, visible_chunks_num, view_matrix, proj_matrix, position, scale, \
-        rotation, opacity, C, S, A, rest_dim, img_h, img_w, true_sigmoid_grad, packed_grad, grad_inv_scaler, g_position, g_scale,       \
+        rotation, opacity, C, S, A, rest_dim, img_h, img_w, true_sigmoid_grad, accumulate, packed_grad, grad_inv_scaler, g_position, g_scale, \
         g_rotation, g_sh_base, g_sh_rest, g_opacity)
     switch (sh_degree) { case 0: PB(0); break; case 1: PB(1); break; case 2: PB(2); break; default: PB(3); }
 #undef PB

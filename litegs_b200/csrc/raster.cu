@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_forward_kernel(
     __shared__ __align__(128) SplatRec s_rec[WARPS_PER_BLOCK][2][32];
     __shared__ __align__(8) uint64_t s_bar[WARPS_PER_BLOCK][2];
     const int lane = threadIdx.x, warp = threadIdx.y, b = blockIdx.y;
-    const int slot = blockIdx.x * WARPS_PER_BLOCK + warp;
+    const int slot = blockIdx.x * blockDim.y + warp;
     int tile_id;
     if (tiles != nullptr) tile_id = (slot < n_sel) ? tiles[(size_t)b * n_sel + slot] : 0;
     else tile_id = slot + 1;
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_kernel(
     __shared__ __align__(128) SplatRec s_rec[WARPS_PER_BLOCK][2][32];
     __shared__ __align__(8) uint64_t s_bar[WARPS_PER_BLOCK][2];
     const int lane = threadIdx.x, warp = threadIdx.y, b = blockIdx.y;
-    const int slot = blockIdx.x * WARPS_PER_BLOCK + warp;
+    const int slot = blockIdx.x * blockDim.y + warp;
     int tile_id;
     if (tiles != nullptr) tile_id = (slot < n_sel) ? tiles[(size_t)b * n_sel + slot] : 0;
     else tile_id = slot + 1;
@@ -460,6 +460,25 @@ static bool use_bulk()
 }
 extern "C" int lgs_set_staging(int bulk) { g_use_bulk = bulk ? 1 : 0; return LGS_OK; }
 
+// warps (= tiles) per CTA for the raster kernels: 1, 2 or 4.  Warps of a CTA are independent (no block-level
+// synchronisation), so this only trades CTA-retirement granularity against launch overhead.
+static int g_wpb = -1;
+static int warps_per_block()
+{
+    if (g_wpb < 0) {
+        const char* e = getenv("LGS_WPB");
+        int v = e ? atoi(e) : 4;
+        g_wpb = (v == 1 || v == 2 || v == 4) ? v : 4;
+    }
+    return g_wpb;
+}
+extern "C" int lgs_set_warps_per_block(int wpb)
+{
+    LGS_REQUIRE(wpb == 1 || wpb == 2 || wpb == 4, "set_warps_per_block: %d not in {1,2,4}", wpb);
+    g_wpb = wpb;
+    return LGS_OK;
+}
+
 extern "C" int lgs_pack_params(const float* ndc, const float* cov2d_inv, const float* color, const float* opacity, int V, int N,
                                int img_h, int img_w, float* packed_params, void* stream)
 {
@@ -484,7 +503,8 @@ extern "C" int lgs_rasterize_forward_packed(const int* sorted_points, const int*
     int ntile = gx * gy, Hp = gy * tile_h, Wp = gx * tile_w;
     int nrender = specific_tiles ? n_specific : ntile;
     if (nrender == 0) return LGS_OK;
-    dim3 grid(lgs_cdiv(nrender, WARPS_PER_BLOCK), V), block(32, WARPS_PER_BLOCK);
+    const int wpb = warps_per_block();
+    dim3 grid(lgs_cdiv(nrender, wpb), V), block(32, wpb);
     cudaStream_t st = (cudaStream_t)stream;
     const SplatRec* recs = (const SplatRec*)packed_params;
     const bool bulk = use_bulk();
@@ -515,7 +535,8 @@ extern "C" int lgs_rasterize_backward(const int* sorted_points, const int* start
     if (N == 0) return LGS_OK;
     LGS_CUDA(cudaMemsetAsync(packed_grad, 0, sizeof(float) * (size_t)V * N * LGS_GRAD_FLOATS, st));
     if (nrender > 0) {
-        dim3 grid(lgs_cdiv(nrender, WARPS_PER_BLOCK), V), block(32, WARPS_PER_BLOCK);
+        const int wpb = warps_per_block();
+        dim3 grid(lgs_cdiv(nrender, wpb), V), block(32, wpb);
         const SplatRec* recs = (const SplatRec*)packed_params;
         const bool bulk = use_bulk();
         const bool trans = d_trans_img != nullptr;

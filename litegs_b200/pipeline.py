@@ -167,10 +167,15 @@ def render_view_forward(params: dict, cluster_origin: torch.Tensor, cluster_exte
 
 
 def render_view_backward(params: dict, state: ViewState, d_img: torch.Tensor, d_trans: Optional[torch.Tensor] = None,
-                         enable_statistic: bool = False, specific_tiles: Optional[torch.Tensor] = None):
+                         enable_statistic: bool = False, specific_tiles: Optional[torch.Tensor] = None,
+                         accumulate_into: Optional[dict] = None):
     """Backward of one view: d_img f32[1,3,Hp,Wp] (padded) -> compacted parameter gradients
     (xyz[3,A,S], scale[3,A,S], rot[4,A,S], sh_0[1,3,A,S], sh_rest[R,3,A,S], opacity[1,A,S]) with
-    A = state.n_chunks_visible, plus packed_grad (whose slot 9 carries the statistics term)."""
+    A = state.n_chunks_visible, plus packed_grad (whose slot 9 carries the statistics term).
+
+    accumulate_into: dict of DENSE contiguous gradient tensors shaped like the parameters; when given, this
+    view's gradients are added into them by the kernel itself and no compacted tensors are produced
+    (returns (None, packed_grad))."""
     xyz = params["xyz"]
     dev = xyz.device
     C, S = xyz.shape[-2:]
@@ -191,6 +196,18 @@ def render_view_backward(params: dict, state: ViewState, d_img: torch.Tensor, d_
         _lib.call("lgs_rasterize_backward", _ptr(state.sorted_pid), _ptr(state.ranges), _ptr(state.packed), _ptr(specific_tiles), n_sel,
                   _ptr(state.T), _ptr(state.last), _ptr(d_img), _ptr(d_trans), None, 1, Nmax, state.sorted_pid.shape[1], H, W, th, tw,
                   int(bool(enable_statistic)), _ptr(pg), None, None, None, None, None, None, st)
+        if accumulate_into is not None:
+            for k in ("xyz", "scale", "rot", "sh_0", "sh_rest", "opacity"):
+                t = accumulate_into[k]
+                if not (t.is_cuda and t.dtype == _F32 and t.is_contiguous() and tuple(t.shape) == tuple(params[k].shape)):
+                    raise RuntimeError(f"accumulate_into['{k}'] must be a contiguous float32 CUDA tensor shaped like the parameter")
+            if A > 0:
+                d = accumulate_into
+                _lib.call("lgs_project_backward", state.sh_degree, _ptr(state.chunk_ids), ctypes.c_void_p(state.counters.data_ptr()),
+                          _ptr(state.view), _ptr(state.proj), _ptr(xyz), _ptr(params["scale"]), _ptr(params["rot"]),
+                          _ptr(params["opacity"]), C, S, A, R, H, W, int(CONFIG["true_sigmoid_grad"]), _ptr(pg), None, 2,
+                          _ptr(d["xyz"]), _ptr(d["scale"]), _ptr(d["rot"]), _ptr(d["sh_0"]), _ptr(d["sh_rest"]), _ptr(d["opacity"]), st)
+            return None, pg
         g_pos = torch.empty((3, A, S), dtype=_F32, device=dev)
         g_sc = torch.empty((3, A, S), dtype=_F32, device=dev)
         g_rot = torch.empty((4, A, S), dtype=_F32, device=dev)

@@ -108,7 +108,7 @@ def render(view_matrix, proj_matrix, xyz, scale, rot, color, opacity,
 class _RenderViewFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xyz, scale, rot, sh_0, sh_rest, opacity, cluster_origin, cluster_extend, frustumplane,
-                view_matrix, proj_matrix, sh_degree, H, W, th, tw, sparse_grad, enable_transmitance):
+                view_matrix, proj_matrix, sh_degree, H, W, th, tw, sparse_grad, enable_transmitance, accumulate_into):
         params = dict(xyz=xyz, scale=scale, rot=rot, sh_0=sh_0, sh_rest=sh_rest, opacity=opacity)
         stat = bool(StatisticsHelperInst.bStart)
         img, state, stats = pipeline.render_view_forward(params, cluster_origin, cluster_extend, frustumplane, view_matrix,
@@ -118,6 +118,7 @@ class _RenderViewFn(torch.autograd.Function):
         ctx.stat = stat
         ctx.sparse = bool(sparse_grad)
         ctx.trans = bool(enable_transmitance)
+        ctx.accumulate_into = accumulate_into
         ctx.save_for_backward(xyz, scale, rot, sh_0, sh_rest, opacity)
         ctx.mark_non_differentiable(state.last)
         return img, state.T, state.last
@@ -129,9 +130,13 @@ class _RenderViewFn(torch.autograd.Function):
         state = ctx.state
         if g_img is None:
             g_img = torch.zeros((1, 3, *state.T.shape[-2:]), dtype=torch.float32, device=xyz.device)
-        grads, pg = pipeline.render_view_backward(params, state, g_img, g_T if ctx.trans else None, enable_statistic=ctx.stat)
+        grads, pg = pipeline.render_view_backward(params, state, g_img, g_T if ctx.trans else None, enable_statistic=ctx.stat,
+                                                  accumulate_into=ctx.accumulate_into)
         if ctx.stat and StatisticsHelperInst.on_fragment_weight is not None:
             StatisticsHelperInst.on_fragment_weight(ctx.stats[1], ctx.stats[0])
+        if grads is None:          # gradients went straight into the caller's dense buffers
+            ctx.state = None
+            return (None,) * 19
         C, S = xyz.shape[-2:]
         ids = state.chunk_ids[: state.n_chunks_visible]
         out = []
@@ -139,24 +144,26 @@ class _RenderViewFn(torch.autograd.Function):
             ct = CompactedTensor((*g.shape[:-2], C, S), ids, g)
             out.append(ct if ctx.sparse else ct.to_dense())
         ctx.state = None
-        return (*out, None, None, None, None, None, None, None, None, None, None, None, None)
+        return (*out, None, None, None, None, None, None, None, None, None, None, None, None, None)
 
 
 def render_view(cluster_origin, cluster_extend, frustumplane, view_matrix, proj_matrix,
-                xyz, scale, rot, sh_0, sh_rest, opacity, actived_sh_degree: int, output_shape, pp):
+                xyz, scale, rot, sh_0, sh_rest, opacity, actived_sh_degree: int, output_shape, pp, accumulate_into=None):
     """render_preprocess + render of one view on the fused pipeline.
 
     Same inputs as the two reference calls (raw clustered parameters, chunk AABBs, camera); returns
     (img [1,3,H,W] clamped to [0,1], transmittance or None, depth=None, normal=None, visible_chunkid,
-    visible_chunks_num).  Gradients reach the six parameter tensors as CompactedTensor (pp.sparse_grad)
-    or dense tensors."""
+    last_contributor).  Gradients reach the six parameter tensors as CompactedTensor (pp.sparse_grad) or dense
+    tensors -- or, with ``accumulate_into`` (dict of dense gradient tensors, e.g. ``GradAccumulator.grads()``), are
+    ADDED into those buffers by the backward kernel itself and ``param.grad`` stays untouched (multi-view batches,
+    data-parallel training)."""
     if not pp.cluster_size:
         raise RuntimeError("render_view needs the clustered layout (cluster_size > 0); use render_preprocess + render otherwise")
     H, W = int(output_shape[0]), int(output_shape[1])
     th, tw = int(pp.tile_size[0]), int(pp.tile_size[1])
     img, T, last = _RenderViewFn.apply(xyz, scale, rot, sh_0, sh_rest, opacity, cluster_origin, cluster_extend, frustumplane,
                                        view_matrix, proj_matrix, int(actived_sh_degree), H, W, th, tw, pp.sparse_grad,
-                                       pp.enable_transmitance)
+                                       pp.enable_transmitance, accumulate_into)
     img = img[..., :H, :W].clamp(0, 1)
     trans = T[..., :H, :W] if pp.enable_transmitance else None
     return img, trans, None, None, last

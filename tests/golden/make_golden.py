@@ -59,39 +59,39 @@ def run_backend(mod, name, torch, dev):
     vis, num, ids = mod.frustum_culling_aabb(T(p["cluster_origin"]), T(p["cluster_extend"]), fp, None, None)
     nvis = int(num.item())
     ids_sorted = torch.sort(ids[:nvis])[0].contiguous()
-    out["cull_vis"] = vis.cpu().numpy(); out["cull_ids"] = ids_sorted.cpu().numpy()
+    out["cull_vis"] = vis.detach().cpu().numpy(); out["cull_ids"] = ids_sorted.detach().cpu().numpy()
     act = mod.cull_compact_activate(deg, ids_sorted, num, view, P["xyz"], P["scale"], P["rot"], P["sh_0"], P["sh_rest"], P["opacity"])
     for k, a in zip(("act_pos", "act_scale", "act_rot", "act_color", "act_opacity"), act):
-        out[k] = a.cpu().numpy()
+        out[k] = a.detach().cpu().numpy()
     xyz, scale, rot, color, opacity = [a.reshape(*a.shape[:-2], -1).contiguous() for a in act]
     vp, ndc = mod.mvp_transform_forward(xyz, view, proj, None)
     Tm = mod.createTransformMatrix_forward(rot, scale, None)
     J = mod.jacobianRayspace(vp, proj, hw[0], hw[1], None)
     cov = mod.createCov2dDirectly_forward(J, view, Tm, None)
     val, vec, inv = mod.eigh_and_inv_2x2matrix_forward(cov, None)
-    out.update(view_pos=vp.cpu().numpy(), ndc=ndc.cpu().numpy(), T=Tm.cpu().numpy(), J=J.cpu().numpy(), cov2d=cov.cpu().numpy(),
-               eig_val=val.cpu().numpy(), inv_cov2d=inv.cpu().numpy())
+    out.update(view_pos=vp.detach().cpu().numpy(), ndc=ndc.detach().cpu().numpy(), T=Tm.detach().cpu().numpy(), J=J.detach().cpu().numpy(), cov2d=cov.detach().cpu().numpy(),
+               eig_val=val.detach().cpu().numpy(), inv_cov2d=inv.detach().cpu().numpy())
     N = xyz.shape[1]
     sl = lambda a: T(a[..., :N])
-    out["bw_inv"] = mod.inv_2x2matrix_backward(inv, sl(up["g_inv"]), None).cpu().numpy()
-    out["bw_cov"] = mod.createCov2dDirectly_backward(sl(up["g_cov"]), J, view, Tm, None).cpu().numpy()
+    out["bw_inv"] = mod.inv_2x2matrix_backward(inv, sl(up["g_inv"]), None).detach().cpu().numpy()
+    out["bw_cov"] = mod.createCov2dDirectly_backward(sl(up["g_cov"]), J, view, Tm, None).detach().cpu().numpy()
     gq, gs = mod.createTransformMatrix_backward(sl(up["g_T"]), rot, scale, None)
-    out["bw_T_q"] = gq.cpu().numpy(); out["bw_T_s"] = gs.cpu().numpy()
-    out["bw_mvp"] = mod.mvp_transform_backward(sl(up["g_ndc"]), sl(up["g_view"]), view, proj, vp, None).cpu().numpy()
+    out["bw_T_q"] = gq.detach().cpu().numpy(); out["bw_T_s"] = gs.detach().cpu().numpy()
+    out["bw_mvp"] = mod.mvp_transform_backward(sl(up["g_ndc"]), sl(up["g_view"]), view, proj, vp, None).detach().cpu().numpy()
     # binning (wrapper.py:718-763 glue)
     vz = vp[:, 2].contiguous()
     lu, rd, alloc = mod.get_allocate_size(ndc, vz, inv, opacity, hw[0], hw[1], tile[0], tile[1], None)
-    out["alloc"] = alloc.cpu().numpy(); out["left_up"] = lu.cpu().numpy(); out["right_down"] = rd.cpu().numpy()
+    out["alloc"] = alloc.detach().cpu().numpy(); out["left_up"] = lu.detach().cpu().numpy(); out["right_down"] = rd.detach().cpu().numpy()
     _, order = vz.sort(dim=-1, descending=False, stable=True)
     prefix = torch.gather(alloc, 1, order).cumsum(1, dtype=torch.int32)
     keys, vals = mod.create_table(ndc, inv, opacity, prefix, order, None, None, hw[0], hw[1], tile[0], tile[1])
     gx, gy = -(-hw[1] // tile[1]), -(-hw[0] // tile[0])
     ranges = mod.tileRange(keys, gx * gy)
-    out["table_keys"] = keys.cpu().numpy(); out["table_vals"] = vals.cpu().numpy(); out["tile_range"] = ranges.cpu().numpy()
+    out["table_keys"] = keys.detach().cpu().numpy(); out["table_vals"] = vals.detach().cpu().numpy(); out["tile_range"] = ranges.detach().cpu().numpy()
     # raster
     r = mod.rasterize_forward(vals, ranges, ndc, inv, color, opacity, None, hw[0], hw[1], tile[0], tile[1], False, False, False)
     img, Tr, _, last, packed = r[0], r[1], r[2], r[3], r[4]
-    out["img"] = img.cpu().numpy(); out["final_T"] = Tr.cpu().numpy(); out["last"] = last.cpu().numpy()
+    out["img"] = img.detach().cpu().numpy(); out["final_T"] = Tr.detach().cpu().numpy(); out["last"] = last.detach().cpu().numpy()
     Hp, Wp = img.shape[-2:]
     d_img = torch.zeros((1, 3, Hp, Wp), device=dev)
     d_img[..., : hw[0], : hw[1]] = T(up["d_img"])
@@ -99,13 +99,13 @@ def run_backend(mod, name, torch, dev):
     b = mod.rasterize_backward(vals, ranges, packed, None, Tr, last, d_img / gmax, None, None, gmax.reshape(1), hw[0], hw[1], tile[0], tile[1],
                                False)
     for k, a in zip(("d_ndc", "d_cov2d_inv", "d_color", "d_opacity"), b[:4]):
-        out[k] = a.cpu().numpy()
+        out[k] = a.detach().cpu().numpy()
     C, S = p["xyz"].shape[-2:]
     A = ids_sorted.shape[0]
     ga = [T(g[..., :A, :]) for g in up["g_act"]]
     ab = mod.activate_backward(deg, ids_sorted, num, view, P["xyz"], P["scale"], P["rot"], P["sh_0"], P["sh_rest"], P["opacity"], *ga)
     for k, a in zip(("ab_pos", "ab_scale", "ab_rot", "ab_sh0", "ab_shr", "ab_opacity"), ab):
-        out[k] = a.cpu().numpy()
+        out[k] = a.detach().cpu().numpy()
     return out
 
 
