@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--level", default="B", choices=["A", "B"], help="B = fused render_view (default), A = op-by-op surface")
     ap.add_argument("--staging", default=None, choices=[None, "bulk", "cpasync"])
+    ap.add_argument("--streams", type=int, default=2, help="CUDA streams the views of a step alternate over (1 = serial)")
     return ap.parse_args()
 
 
@@ -306,12 +307,14 @@ def run_ours(args, rank, world, local_rank):
 
     acc_views = acc.grads()
 
-    def render_one(cam, weight):
+    def render_one(cam, weight, wait_ev=None):
         if args.level == "B":
             # fused path: the backward kernel adds this view's gradients straight into the dense buffer
             img = render.render_view(A[0], A[1], cam["frustumplane"], cam["view"], cam["proj"], P["xyz"], P["scale"], P["rot"],
                                      P["sh_0"], P["sh_rest"], P["opacity"], args.sh_degree, (H, W), pp, accumulate_into=acc_views)[0]
             loss = (img * weight).sum()
+            if wait_ev is not None:      # the dense accumulate of the previous view (other stream) must have landed
+                torch.cuda.current_stream(dev).wait_event(wait_ev)
             loss.backward()
             return loss
         else:
@@ -332,10 +335,33 @@ def run_ours(args, rank, world, local_rank):
             P[k].grad = None
         return loss
 
-    def step():
+    n_streams = max(1, args.streams) if args.level == "B" else 1
+    side = [torch.cuda.Stream(device=dev) for _ in range(n_streams)] if n_streams > 1 else None
+
+    def run_views(view_fn, serial=False):
+        """The views of one step.  With >1 streams consecutive views alternate streams, so view i+1's forward
+        (bandwidth-bound projection/sort kernels + the one host read-back) overlaps view i's backward (issue-bound
+        raster kernel); only the dense gradient accumulate is ordered across views (event)."""
+        if side is None or serial:
+            for j in range(vpr):
+                view_fn(j, None)
+            return
+        cur = torch.cuda.current_stream(dev)
+        for s_ in side:
+            s_.wait_stream(cur)
+        prev = None
+        for j in range(vpr):
+            s_ = side[j % n_streams]
+            with torch.cuda.stream(s_):
+                view_fn(j, prev)
+                prev = torch.cuda.Event()
+                prev.record(s_)
+        for s_ in side:
+            cur.wait_stream(s_)
+
+    def step(serial=False):
         acc.zero_()
-        for c in cams:
-            render_one(c, w)
+        run_views(lambda j, ev: render_one(cams[j], w, ev), serial)
         if world > 1:
             acc.all_reduce()
 
@@ -351,7 +377,6 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    timer.enabled = True
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -359,9 +384,19 @@ def run_ours(args, rank, world, local_rank):
         step()
     e1.record()
     barrier()
-    timer.enabled = False
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
+    # stage attribution / roofline durations: the same steps once more on ONE stream with CUDA events around every
+    # C-ABI call (with overlapping streams a kernel's event-to-event time includes the other stream's work).
+    timer.enabled = True
+    s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(args.steps):
+        step(serial=True)
+    s1.record()
+    barrier()
+    timer.enabled = False
+    ms_serial = s0.elapsed_time(s1)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -389,16 +424,22 @@ def run_ours(args, rank, world, local_rank):
         h2d = sum(v.numel() * v.element_size() for v in cam_host[0].values()) + gt_host[0].numel()
         losses = []
 
+        loss_host = torch.zeros(vpr, dtype=torch.float32).pin_memory()
+
+        def e2e_view(j, ev):
+            cam = {k: v.to(dev, non_blocking=True) for k, v in cam_host[j].items()}
+            gt = gt_host[j % 2].to(dev, non_blocking=True)
+            weight = gt.float() * (1.0 / 255.0) - 0.5
+            loss = render_one(cam, weight, ev)
+            loss_host[j:j + 1].copy_(loss.detach().reshape(1), non_blocking=True)     # D2H read of the view's result
+
         def e2e_step():
             acc.zero_()
-            for j in range(vpr):
-                cam = {k: v.to(dev, non_blocking=True) for k, v in cam_host[j].items()}
-                gt = gt_host[j % 2].to(dev, non_blocking=True)
-                weight = gt.float() * (1.0 / 255.0) - 0.5
-                loss = render_one(cam, weight)
-                losses.append(float(loss.item()))        # D2H read of the step's result
+            run_views(e2e_view)
             if world > 1:
                 acc.all_reduce()
+            torch.cuda.current_stream(dev).synchronize()          # the step's losses are on the host now
+            losses.append(float(loss_host.sum()))
         for _ in range(3):
             e2e_step()
         barrier()
@@ -454,10 +495,11 @@ def run_ours(args, rank, world, local_rank):
     path_bytes = sum(v for k, v in bytes_per.items())
     survey_bytes = 748 * stats["Nv"] + 172 * stats["D"] + 48 * stats["P"]
     ms_view = ms / (vpr * args.steps)
+    ms_view_serial = ms_serial / (vpr * args.steps)
     path = {"alg_bytes_per_view": int(path_bytes), "gbs": path_bytes / (ms_view / 1000.0) / 1e9,
             "frac": path_bytes / (ms_view / 1000.0) / 1e9 / peak_gbs,
             "survey_formula_bytes": int(survey_bytes), "survey_formula_frac": survey_bytes / (ms_view / 1000.0) / 1e9 / peak_gbs,
-            "ms_per_view": ms_view}
+            "ms_per_view": ms_view, "ms_per_view_single_stream": ms_view_serial}
     hand_written = ("lgs_frustum_culling_aabb", "lgs_project_forward", "lgs_emit_pairs", "lgs_tile_range", "lgs_rasterize_forward_packed",
                     "lgs_rasterize_backward", "lgs_project_backward", "lgs_sparse_chunk_op", "lgs_pack_params")
     gpu_launches = 0
@@ -473,7 +515,8 @@ def run_ours(args, rank, world, local_rank):
                                f"{vpr} views/rank/step + dense grad accumulate" + (" + NCCL all-reduce" if world > 1 else ""),
                    "parallelism": f"dp{world} (views sharded, parameters replicated)", "level": args.level,
                    "l2": "inputs exceed L2 (236 MB of parameters streamed per view); no explicit flush",
-                   "staging": args.staging or os.environ.get("LGS_STAGING", "bulk")},
+                   "staging": args.staging or os.environ.get("LGS_STAGING", "default"), "streams": n_streams,
+                   "stage_timing": "serialized pass of the same steps on one stream (CUDA events around every C-ABI call)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches),
         "roofline": roofline, "path_roofline": path, "workload_stats": stats, "stages": stages,
     }

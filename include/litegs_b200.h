@@ -167,7 +167,7 @@ int lgs_rasterize_backward(const int* sorted_points, const int* start_index, con
                            int tile_w, int enable_statistic, float* packed_grad, float* d_ndc, float* d_cov2d_inv,
                            float* d_color, float* d_opacity, float* err_sum, float* err_square_sum, void* stream);
 
-/* staging selector for the raster kernels: 1 = cp.async.bulk + mbarrier (default), 0 = cp.async */
+/* staging selector for the raster kernels: 0 = cp.async / LDGSTS (default, measured faster), 1 = cp.async.bulk + mbarrier */
 int lgs_set_staging(int bulk);
 /* tiles (warps) per CTA of the raster kernels: 1, 2 or 4 (default 4, env LGS_WPB) */
 int lgs_set_warps_per_block(int wpb);

@@ -7,10 +7,10 @@
 //    FMAs per pixel; transmittance, colour and the contributor count live in registers;
 //  * the tile's depth-sorted splat list is consumed in chunks of 32: lane i fetches id i of the chunk
 //    (one coalesced 128-byte row of the index list) and stages that splat's 48-byte fp32 record into
-//    shared memory with an asynchronous copy -- either three 16-byte cp.async (LDGSTS) or one 48-byte
-//    cp.async.bulk (UBLKCP, the TMA engine's 1-D bulk copy) completing on an mbarrier; two buffers per
-//    warp, so chunk c+1 is in flight while chunk c is blended; records are then read back as
-//    conflict-free broadcast LDS.128;
+//    shared memory with an asynchronous copy -- either three 16-byte cp.async (LDGSTS, the default: measured
+//    faster for this per-lane gather) or one 48-byte cp.async.bulk (UBLKCP, the TMA engine's 1-D bulk copy)
+//    completing on an mbarrier; two buffers per warp, so chunk c+1 is in flight while chunk c is blended;
+//    records are then read back as conflict-free broadcast LDS.128;
 //  * fp32 throughout (ex2.approx.ftz for the Gaussian): the 1e-4 parity gate of BASELINE.json rules out
 //    the reference's packed-half blend;
 //  * backward: per-(tile, splat) gradients are reduced over the tile's pixels entirely inside the warp
@@ -36,6 +36,29 @@ __device__ __forceinline__ float fast_rcp(float x)
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+// One pixel of the front-to-back blend as straight predicated code (no branches, no selects):
+//   act = Ts > TS_MIN ; n += act ; ok = act && a >= A_MIN ; if ok { w = a*Ts ; C += c*w ; Ts -= (255/256) w }
+// Written in PTX so that ptxas keeps it as 2 SETP + 6 predicated FMA-pipe ops instead of re-introducing
+// BSSY/BRA/BSYNC around each pixel or spending half-rate ALU-pipe selects.
+__device__ __forceinline__ void blend_pixel(float a, float cr, float cg, float cb, float& Ts, float& Cr, float& Cg, float& Cb,
+                                            float& nf, float ts_min, float a_min, float neg_ki)
+{
+    asm("{\n"
+        ".reg .pred pa, pk;\n"
+        ".reg .f32 w;\n"
+        "setp.gt.f32 pa, %0, %9;\n"
+        "@pa add.f32 %4, %4, 0f3F800000;\n"
+        "setp.ge.and.f32 pk, %5, %10, pa;\n"
+        "mul.f32 w, %5, %0;\n"
+        "@pk fma.rn.f32 %1, %6, w, %1;\n"
+        "@pk fma.rn.f32 %2, %7, w, %2;\n"
+        "@pk fma.rn.f32 %3, %8, w, %3;\n"
+        "@pk fma.rn.f32 %0, %11, w, %0;\n"
+        "}\n"
+        : "+f"(Ts), "+f"(Cr), "+f"(Cg), "+f"(Cb), "+f"(nf)
+        : "f"(a), "f"(cr), "f"(cg), "f"(cb), "f"(ts_min), "f"(a_min), "f"(neg_ki));
 }
 
 // ---- asynchronous staging primitives -------------------------------------------------------------
@@ -190,10 +213,14 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_forward_kernel(
     const int y0 = ((tile_id - 1) / gx) * TH + (lane / TW) * PPT;
     const float fx = (float)x, fy0 = (float)y0;
 
-    float T[PPT], Cr[PPT], Cg[PPT], Cb[PPT];
-    int n[PPT];
+    // State per pixel: Ts = T * 255/256 (so that the reference's "alpha = min(alpha, 255/256)" becomes the free
+    // saturate of one FMUL.SAT on alpha * 256/255), colour, and the visited-while-active count as a float
+    // (exact up to 2^24; a predicated FADD on the FMA pipe instead of integer ops on the half-rate ALU pipe).
+    constexpr float KS = 256.0f / 255.0f, KI = 255.0f / 256.0f;
+    constexpr float TS_MIN = T_MIN * KI, A_MIN_S = ALPHA_MIN * KS;
+    float Ts[PPT], Cr[PPT], Cg[PPT], Cb[PPT], nf[PPT];
 #pragma unroll
-    for (int j = 0; j < PPT; j++) { T[j] = 1.0f; Cr[j] = Cg[j] = Cb[j] = 0.0f; n[j] = 0; }
+    for (int j = 0; j < PPT; j++) { Ts[j] = KI; Cr[j] = Cg[j] = Cb[j] = 0.0f; nf[j] = 0.0f; }
 
     if (count > 0) {
         Stager<BULK> st;
@@ -216,32 +243,32 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_forward_kernel(
             int my_id = 0;
             if (STAT) my_id = ids[c * 32 + min(lane, nk - 1)];
             for (int k = 0; k < nk; k++) {
-                bool lane_active = false;
+                if ((k & 3) == 0) {
+                    // tile-wide early out, tested every 4th splat: a saturated pixel blends nothing and counts
+                    // nothing, so running up to 3 splats past the point where the last pixel saturates is exact.
+                    float tmax = Ts[0];
 #pragma unroll
-                for (int j = 0; j < PPT; j++) lane_active |= (T[j] > T_MIN);
-                if (!__any_sync(FULL_MASK, lane_active)) { done = true; break; }
+                    for (int j = 1; j < PPT; j++) tmax = fmaxf(tmax, Ts[j]);
+                    if (!__any_sync(FULL_MASK, tmax > TS_MIN)) { done = true; break; }
+                }
                 const float4 q0 = *reinterpret_cast<const float4*>(&chunk[k].px);   // px py A B
                 const float4 q1 = *reinterpret_cast<const float4*>(&chunk[k].C);    // C o r g
                 const float cb = chunk[k].b;
                 const float dx = q0.x - fx, dy0 = q0.y - fy0;
                 const float a2 = (-0.5f * LOG2E) * q0.z, b2 = (-LOG2E) * q0.w, c2 = (-0.5f * LOG2E) * q1.x;
                 const float base = a2 * dx * dx, lin = b2 * dx;
+                const float os = q1.y * KS;
                 int fcount = 0; float wsum = 0.f;
 #pragma unroll
                 for (int j = 0; j < PPT; j++) {
                     const float dy = dy0 - (float)j;
                     const float pw = fmaf(dy, fmaf(c2, dy, lin), base);
-                    float alpha = q1.y * fast_ex2(pw);
-                    const bool act = T[j] > T_MIN;
-                    n[j] += act ? 1 : 0;
-                    const bool ok = act && (alpha >= ALPHA_MIN);
-                    alpha = fminf(alpha, ALPHA_MAX);
-                    const float w = ok ? alpha * T[j] : 0.0f;
-                    Cr[j] = fmaf(q1.z, w, Cr[j]);
-                    Cg[j] = fmaf(q1.w, w, Cg[j]);
-                    Cb[j] = fmaf(cb, w, Cb[j]);
-                    T[j] -= w;
-                    if (STAT) { fcount += ok ? 1 : 0; wsum += w; }
+                    const float a = __saturatef(os * fast_ex2(pw));          // min(alpha, 255/256) * 256/255
+                    if (STAT) {
+                        const bool ok = (Ts[j] > TS_MIN) && (a >= A_MIN_S);
+                        if (ok) { fcount++; wsum += a * Ts[j]; }
+                    }
+                    blend_pixel(a, q1.z, q1.w, cb, Ts[j], Cr[j], Cg[j], Cb[j], nf[j], TS_MIN, A_MIN_S, -KI);
                 }
                 if (STAT) {
                     // per-(tile,splat) fragment statistics for densification (GR/raster.cu:288-301)
@@ -267,8 +294,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_forward_kernel(
         img[((size_t)b * 3 + 0) * plane + po] = fminf(Cr[j], 1.0f);
         img[((size_t)b * 3 + 1) * plane + po] = fminf(Cg[j], 1.0f);
         img[((size_t)b * 3 + 2) * plane + po] = fminf(Cb[j], 1.0f);
-        Tout[(size_t)b * plane + po] = T[j];
-        last[(size_t)b * plane + po] = (short)n[j];
+        Tout[(size_t)b * plane + po] = Ts[j] * KS;
+        last[(size_t)b * plane + po] = (short)(int)nf[j];
     }
 }
 
@@ -453,8 +480,10 @@ static int g_use_bulk = -1;
 static bool use_bulk()
 {
     if (g_use_bulk < 0) {
-        const char* e = getenv("LGS_STAGING");     // "bulk" (default) | "cpasync"
-        g_use_bulk = (e && e[0] == 'c') ? 0 : 1;
+        // "cpasync" (default: measured 12-20 % faster on B200 for this 48-byte-per-lane gather, profiles/sweep_r1.txt)
+        // | "bulk" (cp.async.bulk + mbarrier)
+        const char* e = getenv("LGS_STAGING");
+        g_use_bulk = (e && e[0] == 'b') ? 1 : 0;
     }
     return g_use_bulk == 1;
 }
