@@ -306,62 +306,37 @@ def run_ours(args, rank, world, local_rank):
     launches = {"n": 0}
 
     acc_views = acc.grads()
+    n_streams = max(1, args.streams) if args.level == "B" else 1
 
-    def render_one(cam, weight, wait_ev=None):
-        if args.level == "B":
-            # fused path: the backward kernel adds this view's gradients straight into the dense buffer
-            img = render.render_view(A[0], A[1], cam["frustumplane"], cam["view"], cam["proj"], P["xyz"], P["scale"], P["rot"],
-                                     P["sh_0"], P["sh_rest"], P["opacity"], args.sh_degree, (H, W), pp, accumulate_into=acc_views)[0]
-            loss = (img * weight).sum()
-            if wait_ev is not None:      # the dense accumulate of the previous view (other stream) must have landed
-                torch.cuda.current_stream(dev).wait_event(wait_ev)
-            loss.backward()
-            return loss
-        else:
-            ids, num, cx, cs, cr, col, cop = render.render_preprocess(A[0], A[1], cam["frustumplane"], cam["view"], P["xyz"], P["scale"],
-                                                                      P["rot"], P["sh_0"], P["sh_rest"], P["opacity"], None, None, pp,
-                                                                      args.sh_degree)
-            img = render.render(cam["view"], cam["proj"], cx, cs, cr, col, cop, num * pp.cluster_size, None, None, args.sh_degree,
-                                (H, W), pp)[0]
+    def render_one_level_a(cam, weight):
+        ids, num, cx, cs, cr, col, cop = render.render_preprocess(A[0], A[1], cam["frustumplane"], cam["view"], P["xyz"], P["scale"],
+                                                                  P["rot"], P["sh_0"], P["sh_rest"], P["opacity"], None, None, pp,
+                                                                  args.sh_degree)
+        img = render.render(cam["view"], cam["proj"], cx, cs, cr, col, cop, num * pp.cluster_size, None, None, args.sh_degree,
+                            (H, W), pp)[0]
         loss = (img * weight).sum()
         loss.backward()
-        g0 = P["xyz"].grad
-        ids = g0.chunk_ids
-        cnt = torch.tensor([ids.shape[0]], dtype=torch.int32, device=dev) if args.level == "A" else None
-        if cnt is None:
-            cnt = torch.full((1,), ids.shape[0], dtype=torch.int32, device=dev)
-        acc.add_view({k: P[k].grad.compacted_values for k in PARAM_KEYS}, ids, cnt)
+        ids_ = P["xyz"].grad.chunk_ids
+        cnt = torch.full((1,), ids_.shape[0], dtype=torch.int32, device=dev)
+        acc.add_view({k: P[k].grad.compacted_values for k in PARAM_KEYS}, ids_, cnt)
         for k in PARAM_KEYS:
             P[k].grad = None
-        return loss
+        return loss.detach()
 
-    n_streams = max(1, args.streams) if args.level == "B" else 1
-    side = [torch.cuda.Stream(device=dev) for _ in range(n_streams)] if n_streams > 1 else None
-
-    def run_views(view_fn, serial=False):
-        """The views of one step.  With >1 streams consecutive views alternate streams, so view i+1's forward
-        (bandwidth-bound projection/sort kernels + the one host read-back) overlaps view i's backward (issue-bound
-        raster kernel); only the dense gradient accumulate is ordered across views (event)."""
-        if side is None or serial:
-            for j in range(vpr):
-                view_fn(j, None)
-            return
-        cur = torch.cuda.current_stream(dev)
-        for s_ in side:
-            s_.wait_stream(cur)
-        prev = None
-        for j in range(vpr):
-            s_ = side[j % n_streams]
-            with torch.cuda.stream(s_):
-                view_fn(j, prev)
-                prev = torch.cuda.Event()
-                prev.record(s_)
-        for s_ in side:
-            cur.wait_stream(s_)
+    def run_views(camera_fn, loss_fn, serial=False):
+        """One step's views through the public API: litegs_b200.render.render_views (fused level B: views pipelined over
+        CUDA streams, gradients accumulated into the dense buffer by the backward kernel) or the op-by-op level A."""
+        if args.level == "B":
+            return render.render_views(vpr, camera_fn, loss_fn, A[0], A[1], P["xyz"], P["scale"], P["rot"], P["sh_0"], P["sh_rest"],
+                                       P["opacity"], args.sh_degree, (H, W), pp, acc_views, n_streams=1 if serial else n_streams)
+        return [render_one_level_a(camera_fn(j), loss_fn(j, None)) for j in range(vpr)]
 
     def step(serial=False):
         acc.zero_()
-        run_views(lambda j, ev: render_one(cams[j], w, ev), serial)
+        if args.level == "B":
+            run_views(lambda j: cams[j], lambda j, img: (img * w).sum(), serial)
+        else:
+            run_views(lambda j: cams[j], lambda j, img: w, serial)
         if world > 1:
             acc.all_reduce()
 
@@ -426,19 +401,26 @@ def run_ours(args, rank, world, local_rank):
 
         loss_host = torch.zeros(vpr, dtype=torch.float32).pin_memory()
 
-        def e2e_view(j, ev):
-            cam = {k: v.to(dev, non_blocking=True) for k, v in cam_host[j].items()}
+        def e2e_camera(j):          # H2D of the view's camera, on the view's stream
+            return {k: v.to(dev, non_blocking=True) for k, v in cam_host[j].items()}
+
+        def e2e_loss(j, img):       # H2D of the uint8 target, loss, D2H of the result
             gt = gt_host[j % 2].to(dev, non_blocking=True)
             weight = gt.float() * (1.0 / 255.0) - 0.5
-            loss = render_one(cam, weight, ev)
-            loss_host[j:j + 1].copy_(loss.detach().reshape(1), non_blocking=True)     # D2H read of the view's result
+            if img is None:
+                return weight
+            loss = (img * weight).sum()
+            loss_host[j:j + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+            return loss
 
         def e2e_step():
             acc.zero_()
-            run_views(e2e_view)
+            out = run_views(e2e_camera, e2e_loss)
             if world > 1:
                 acc.all_reduce()
             torch.cuda.current_stream(dev).synchronize()          # the step's losses are on the host now
+            if args.level == "A":
+                loss_host.copy_(torch.stack(out).reshape(-1))
             losses.append(float(loss_host.sum()))
         for _ in range(3):
             e2e_step()
@@ -512,7 +494,7 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": f"{args.gaussians} Gaussians (seed 0), {W}x{H}, sh_degree {args.sh_degree}, tile {args.tile}, "
-                               f"{vpr} views/rank/step + dense grad accumulate" + (" + NCCL all-reduce" if world > 1 else ""),
+                               f"{vpr} views/rank/step (render_views) + dense grad accumulate" + (" + NCCL all-reduce" if world > 1 else ""),
                    "parallelism": f"dp{world} (views sharded, parameters replicated)", "level": args.level,
                    "l2": "inputs exceed L2 (236 MB of parameters streamed per view); no explicit flush",
                    "staging": args.staging or os.environ.get("LGS_STAGING", "default"), "streams": n_streams,

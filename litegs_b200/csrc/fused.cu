@@ -144,7 +144,8 @@ __global__ void project_forward_kernel(
         r.px = __fsub_rn(__fmul_rn(__fmul_rn(__fadd_rn(ndcx, 1.0f), 0.5f), (float)W), 0.5f);   // GR/raster.cu:347-348
         r.py = __fsub_rn(__fmul_rn(__fmul_rn(__fadd_rn(ndcy, 1.0f), 0.5f), (float)H), 0.5f);
         r.A = t.inv[0]; r.B = t.inv[1]; r.C = t.inv[2]; r.o = t.o;
-        r.r = col[0]; r.g = col[1]; r.b = col[2]; r.depth = ndcz; r.pad0 = ndcx; r.pad1 = ndcy;
+        r.r = col[0]; r.g = col[1]; r.b = col[2]; r.depth = t.v[2]; r.pad0 = ndcx; r.pad1 = ndcy;   // depth slot: view-space z (the sort key)
+        (void)ndcz;
     }
     recs[dst] = r;
     depth_key[dst] = key;

@@ -246,6 +246,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_forward_kernel(
                 if ((k & 3) == 0) {
                     // tile-wide early out, tested every 4th splat: a saturated pixel blends nothing and counts
                     // nothing, so running up to 3 splats past the point where the last pixel saturates is exact.
+                    // (Skipping individual saturated pixel ROWS with warp-uniform branches was measured 35-65 % SLOWER:
+                    //  the branches serialise the 8 independent pixel chains the scheduler otherwise interleaves.)
                     float tmax = Ts[0];
 #pragma unroll
                     for (int j = 1; j < PPT; j++) tmax = fmaxf(tmax, Ts[j]);

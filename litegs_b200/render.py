@@ -167,3 +167,61 @@ def render_view(cluster_origin, cluster_extend, frustumplane, view_matrix, proj_
     img = img[..., :H, :W].clamp(0, 1)
     trans = T[..., :H, :W] if pp.enable_transmitance else None
     return img, trans, None, None, last
+
+
+# ---------------------------------------------------------------------------------------------------
+# multi-view micro-batch: views pipelined over CUDA streams, gradients summed in dense buffers
+# ---------------------------------------------------------------------------------------------------
+
+_side_streams: dict = {}
+
+
+def _streams(dev, n):
+    key = (dev, n)
+    if key not in _side_streams:
+        _side_streams[key] = [torch.cuda.Stream(device=dev) for _ in range(n)]
+    return _side_streams[key]
+
+
+def render_views(n_views: int, camera_fn, loss_fn, cluster_origin, cluster_extend,
+                 xyz, scale, rot, sh_0, sh_rest, opacity, actived_sh_degree: int, output_shape, pp,
+                 accumulate_into: dict, n_streams: int = 3):
+    """Forward + backward of a batch of views with the gradients summed into ``accumulate_into`` (dense tensors shaped
+    like the parameters, e.g. ``GradAccumulator.grads()``).  This is the per-rank body of a data-parallel step.
+
+    ``camera_fn(i)`` -> dict(view, proj, frustumplane) and ``loss_fn(i, img)`` -> scalar loss are called with view i's
+    stream current (so H2D copies issued inside them are ordered correctly).  Consecutive views alternate over
+    ``n_streams`` CUDA streams: view i+1's forward (bandwidth-bound projection / sort kernels and the one host
+    read-back) overlaps view i's backward (issue-bound raster kernel).  Views only interact through the dense
+    accumulate, which is ordered by an event.  Returns the list of (detached) per-view losses."""
+    dev = xyz.device
+    losses = []
+
+    def one(i, wait_ev):
+        cam = camera_fn(i)
+        img = render_view(cluster_origin, cluster_extend, cam["frustumplane"], cam["view"], cam["proj"], xyz, scale, rot, sh_0, sh_rest,
+                          opacity, actived_sh_degree, output_shape, pp, accumulate_into=accumulate_into)[0]
+        loss = loss_fn(i, img)
+        if wait_ev is not None:          # the previous view's accumulate (other stream) must have landed
+            torch.cuda.current_stream(dev).wait_event(wait_ev)
+        loss.backward()
+        losses.append(loss.detach())
+
+    if n_streams <= 1:
+        for i in range(n_views):
+            one(i, None)
+        return losses
+    cur = torch.cuda.current_stream(dev)
+    side = _streams(dev, n_streams)
+    for s in side:
+        s.wait_stream(cur)
+    prev = None
+    for i in range(n_views):
+        s = side[i % n_streams]
+        with torch.cuda.stream(s):
+            one(i, prev)
+            prev = torch.cuda.Event()
+            prev.record(s)
+    for s in side:
+        cur.wait_stream(s)
+    return losses

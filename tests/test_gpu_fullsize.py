@@ -1,0 +1,138 @@
+"""BASELINE.json full-size configurations on the GPU, checked through size-independent properties (the CPU oracle
+cannot finish these in seconds): C2 = 1M Gaussians @1080p, C4 = 5M Gaussians @4K (tile-overflow / sort-bound stress).
+
+ * per-tile lists: keys sorted by tile, depth ascending inside every tile, D == sum of per-splat tile counts;
+ * forward is deterministic (bit-identical image twice), img <= 1 and finite, 0 < T <= 1, last_contributor <= list length;
+ * the backward is LINEAR in dL/dimg: grads(a*g1 + b*g2) == a*grads(g1) + b*grads(g2);
+ * Level A (op by op) and Level B (fused) agree at full size;
+ * the sparse Adam step changes exactly the visible chunks."""
+import numpy as np
+import pytest
+import torch
+
+from litegs_b200 import fused, pipeline, render, scene
+from litegs_b200.arguments import PipelineParams
+
+pytestmark = pytest.mark.gpu
+KEYS = ("xyz", "scale", "rot", "sh_0", "sh_rest", "opacity")
+
+
+def _scene(n, dev, seed=0, log_scale_range=(0.002, 0.02)):
+    p = scene.make_scene(n, sh_degree=3, seed=seed, log_scale_range=log_scale_range)
+    P = {k: torch.from_numpy(p[k]).to(dev) for k in KEYS}
+    A = [torch.from_numpy(p[k]).to(dev) for k in ("cluster_origin", "cluster_extend")]
+    return P, A
+
+
+def _cam(i, n, W, H, dev):
+    return {k: torch.from_numpy(v).to(dev) for k, v in scene.make_camera(i, n, W, H).items()}
+
+
+def _list_properties(st, S):
+    D = st.n_pairs
+    assert D == int(st.tile_count[: st.n_chunks_visible * S].sum().item())
+    ranges = st.ranges[0].long()
+    ntile = ranges.shape[0] - 2
+    start, end = ranges[1:ntile + 1], ranges[2:ntile + 2]
+    pop = (start >= 0) & (end > start)
+    assert int((end[pop] - start[pop]).sum().item()) == D
+    # depth ascending inside every tile: compare neighbours that belong to the same tile
+    z = st.packed[0, :, 9]                       # depth slot of the fused record = view-space z, the sort key
+    pid = st.sorted_pid[0].long()
+    tile_of = torch.zeros(D, dtype=torch.long, device=pid.device)
+    tile_of[start[pop]] = 1
+    tile_of = tile_of.cumsum(0)
+    same = tile_of[1:] == tile_of[:-1]
+    dz = z[pid[1:]] - z[pid[:-1]]
+    assert bool((dz[same] >= 0).all())
+    return start, end, pop
+
+
+@pytest.mark.parametrize("tile", [(16, 16), (8, 16)])
+def test_c2_1m_1080p_properties(cuda, tile):
+    H, W = 1080, 1920
+    P, A = _scene(1_000_000, cuda)
+    cam = _cam(0, 64, W, H, cuda)
+    S = P["xyz"].shape[-1]
+    img, st, _ = pipeline.render_view_forward(P, A[0], A[1], cam["frustumplane"], cam["view"], cam["proj"], 3, (H, W), tile)
+    img2, st2, _ = pipeline.render_view_forward(P, A[0], A[1], cam["frustumplane"], cam["view"], cam["proj"], 3, (H, W), tile)
+    assert torch.equal(img, img2) and torch.equal(st.last, st2.last) and torch.equal(st.sorted_pid, st2.sorted_pid)
+    # the kernel applies min(c,1) only; negative SH colours are legal on the cluster path, render() clamps
+    assert float(img.max()) <= 1.0 and bool(torch.isfinite(img).all())
+    assert float(st.T.min()) > 0.0 and float(st.T.max()) <= 1.0
+    start, end, pop = _list_properties(st, S)
+    gy, gx = -(-H // tile[0]), -(-W // tile[1])
+    lens = torch.where(pop, end - start, torch.zeros_like(end)).reshape(gy, gx)
+    last = st.last[0, 0].long().reshape(gy, tile[0], gx, tile[1]).amax(dim=(1, 3))
+    assert bool((last <= lens).all())
+    assert st.n_pairs > 1_000_000 and float(st.last.float().mean()) > 10
+    # linearity of the backward in dL/dimg
+    g = torch.Generator(device="cpu").manual_seed(0)
+    g1 = torch.randn(img.shape, generator=g).to(cuda); g2 = torch.randn(img.shape, generator=g).to(cuda)
+    a, b = 0.7, -1.3
+    r1, _ = pipeline.render_view_backward(P, st, g1)
+    r2, _ = pipeline.render_view_backward(P, st, g2)
+    r3, _ = pipeline.render_view_backward(P, st, a * g1 + b * g2)
+    for x1, x2, x3 in zip(r1, r2, r3):
+        ref = a * x1 + b * x2
+        scale = float(ref.abs().max()) + 1e-30
+        assert float((x3 - ref).abs().max()) / scale < 2e-4
+
+
+def test_c2_level_a_equals_level_b(cuda):
+    H, W = 1080, 1920
+    P, A = _scene(1_000_000, cuda)
+    cam = _cam(5, 64, W, H, cuda)
+    pp = PipelineParams(tile_size=(8, 16))
+    w = torch.randn((1, 3, H, W), generator=torch.Generator(device="cpu").manual_seed(2)).to(cuda)
+    outs = []
+    for level in ("A", "B"):
+        Q = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+        if level == "A":
+            ids, num, cx, cs, cr, col, cop = render.render_preprocess(A[0], A[1], cam["frustumplane"], cam["view"], Q["xyz"], Q["scale"],
+                                                                      Q["rot"], Q["sh_0"], Q["sh_rest"], Q["opacity"], None, None, pp, 3)
+            img = render.render(cam["view"], cam["proj"], cx, cs, cr, col, cop, num * 128, None, None, 3, (H, W), pp)[0]
+        else:
+            img = render.render_view(A[0], A[1], cam["frustumplane"], cam["view"], cam["proj"], Q["xyz"], Q["scale"], Q["rot"], Q["sh_0"],
+                                     Q["sh_rest"], Q["opacity"], 3, (H, W), pp)[0]
+        (img * w).sum().backward()
+        outs.append((img.detach(), {k: Q[k].grad.compacted_values for k in KEYS}))
+    assert float((outs[0][0] - outs[1][0]).abs().max()) < 2e-5
+    for k in KEYS:
+        a, b = outs[0][1][k], outs[1][1][k]
+        assert float((a - b).abs().max()) / (float(a.abs().max()) + 1e-30) < 2e-4, k
+
+
+def test_c4_5m_4k_stress(cuda):
+    """5M Gaussians at 3840x2160: 32,400 16x16 tiles, tens of millions of pairs; int16 contributor counts must not
+    overflow and the tile lists must stay consistent."""
+    H, W = 2160, 3840
+    lo, hi = 0.002 * np.exp(-0.5), 0.02 * np.exp(-0.5)            # log-scales shifted by -0.5
+    P, A = _scene(5_000_000, cuda, seed=0, log_scale_range=(lo, hi))
+    cam = _cam(0, 64, W, H, cuda)
+    S = P["xyz"].shape[-1]
+    img, st, _ = pipeline.render_view_forward(P, A[0], A[1], cam["frustumplane"], cam["view"], cam["proj"], 3, (H, W), (16, 16))
+    assert st.n_pairs > 10_000_000
+    _list_properties(st, S)
+    assert int(st.last.min()) >= 0 and int(st.last.max()) < 32767
+    assert float(img.max()) <= 1.0 and bool(torch.isfinite(img).all())
+    grads, _ = pipeline.render_view_backward(P, st, torch.ones_like(img))
+    assert all(bool(torch.isfinite(g).all()) for g in grads)
+    assert float(grads[3].abs().sum()) > 0
+
+
+def test_sparse_adam_touches_only_visible_chunks(cuda):
+    P, A = _scene(20_000, cuda)
+    C, S = P["xyz"].shape[-2:]
+    param = P["scale"].clone()
+    before = param.clone()
+    ids = torch.tensor([1, 5, 7, 0], dtype=torch.int64, device=cuda)      # last entry beyond valid_length
+    vl = torch.tensor([3], dtype=torch.int32, device=cuda)
+    grad = torch.randn((3, 4, S), device=cuda)
+    m = torch.zeros_like(param); v = torch.zeros_like(param)
+    fused.adamUpdate(param, grad, m, v, ids, vl, 0.01, 0.9, 0.999, 1e-15)
+    changed = (param != before).any(dim=0).any(dim=-1).nonzero().flatten().tolist()
+    assert changed == [1, 5, 7]
+    # Adam without bias correction (GR/compact.cu:333-338)
+    e1 = 0.1 * grad[:, 0]; e2 = 0.001 * grad[:, 0] ** 2
+    assert torch.allclose(param[:, 1], before[:, 1] - 0.01 * e1 / (e2.sqrt() + 1e-15), rtol=1e-5, atol=1e-7)

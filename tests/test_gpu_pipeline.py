@@ -163,3 +163,27 @@ def test_accumulate_into_dense_buffers_equals_sum_of_views(cuda):
     got = acc.grads()
     for k in PARAM_KEYS:
         assert scaled_err(got[k].cpu().numpy(), dense_ref[k].cpu().numpy()) < 1e-6, k
+
+
+def test_render_views_streams_match_serial(cuda):
+    """render_views: pipelining the views of a batch over 3 CUDA streams gives the same accumulated gradients and losses
+    as running them one after the other."""
+    from litegs_b200 import scene
+    from litegs_b200.dist import GradAccumulator
+    hw, tile = (72, 96), (8, 16)
+    p = scene.make_scene(8000, sh_degree=3, cube=1.5, seed=6, log_scale_range=(0.02, 0.08))
+    params = {k: p[k] for k in PARAM_KEYS}
+    pp = PipelineParams(tile_size=tile)
+    P, A, _ = _to_torch(params, (p["cluster_origin"], p["cluster_extend"]), scene.make_camera(0, 8, hw[1], hw[0]), cuda)
+    cams = [{k: torch.from_numpy(x).to(cuda) for k, x in scene.make_camera(v, 8, hw[1], hw[0]).items()} for v in range(6)]
+    w = torch.from_numpy(np.random.default_rng(0).normal(size=(1, 3, *hw)).astype(np.float32)).to(cuda)
+    res = []
+    for ns in (1, 3):
+        acc = GradAccumulator(P)
+        losses = render.render_views(6, lambda i: cams[i], lambda i, img: (img * w).sum() * (1.0 + 0.1 * i), A[0], A[1], P["xyz"], P["scale"],
+                                     P["rot"], P["sh_0"], P["sh_rest"], P["opacity"], 3, hw, pp, acc.grads(), n_streams=ns)
+        torch.cuda.synchronize()
+        res.append(([float(x) for x in losses], {k: v.clone() for k, v in acc.grads().items()}))
+    assert np.allclose(res[0][0], res[1][0], rtol=1e-6)
+    for k in PARAM_KEYS:
+        assert scaled_err(res[1][1][k].cpu().numpy(), res[0][1][k].cpu().numpy()) < 1e-5, k
