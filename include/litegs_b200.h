@@ -133,7 +133,13 @@ int lgs_create_table(const float* ndc, const float* inv_cov2d, const float* opac
 int lgs_tile_range(const int* table_tile_id, int V, int table_length, int max_tile_id, int fix_last, int* tile_range,
                    void* stream);
 
+int lgs_tile_range_u16(const unsigned short* table_tile_id, int V, int table_length, int max_tile_id, int fix_last,
+                       int* tile_range, void* stream);
+
 /* building blocks of the fused pipeline (cub radix sort / scan on the caller's stream and workspace) */
+int lgs_sort_pairs_u16_workspace_bytes(int n, size_t* bytes);
+int lgs_sort_pairs_u16(const unsigned short* keys_in, unsigned short* keys_out, const unsigned* vals_in, unsigned* vals_out,
+                       int n, int begin_bit, int end_bit, void* workspace, size_t workspace_bytes, void* stream);
 int lgs_sort_pairs_u32_workspace_bytes(int n, size_t* bytes);
 int lgs_sort_pairs_u32(const unsigned* keys_in, unsigned* keys_out, const unsigned* vals_in, unsigned* vals_out, int n,
                        int begin_bit, int end_bit, void* workspace, size_t workspace_bytes, void* stream);
@@ -191,6 +197,9 @@ int lgs_project_forward(int sh_degree, const int64_t* visible_chunk_id, const in
  * counts, order = depth-sorted slot ids; keys/vals i32[cap] must be zero-initialised by the caller. */
 int lgs_emit_pairs(const float* packed_params, const int* offset, const unsigned* order, int n, int cap, int img_h,
                    int img_w, int tile_h, int tile_w, int* keys, int* vals, void* stream);
+/* same with 16-bit tile keys (tiles + 1 < 65536): 25 % fewer bytes through emit, the tile sort and tile_range */
+int lgs_emit_pairs_u16(const float* packed_params, const int* offset, const unsigned* order, int n, int cap, int img_h,
+                       int img_w, int tile_h, int tile_w, unsigned short* keys, int* vals, void* stream);
 
 /* Record gradient (packed_grad f32[A*S,12] from lgs_rasterize_backward) -> the six compacted parameter gradients;
  * replaces unpack_gradient + inv_2x2matrix_backward(+nan_to_num) + createCov2dDirectly_backward +

@@ -34,6 +34,10 @@ SIGNATURES = {
     "lgs_create_table_workspace_bytes": [_I, _I, ctypes.POINTER(_Z)],
     "lgs_create_table": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _Z, _P],
     "lgs_tile_range": [_P, _I, _I, _I, _I, _P, _P],
+    "lgs_tile_range_u16": [_P, _I, _I, _I, _I, _P, _P],
+    "lgs_sort_pairs_u16_workspace_bytes": [_I, ctypes.POINTER(_Z)],
+    "lgs_sort_pairs_u16": [_P, _P, _P, _P, _I, _I, _I, _P, _Z, _P],
+    "lgs_emit_pairs_u16": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "lgs_sort_pairs_u32_workspace_bytes": [_I, ctypes.POINTER(_Z)],
     "lgs_sort_pairs_u32": [_P, _P, _P, _P, _I, _I, _I, _P, _Z, _P],
     "lgs_scan_gathered_workspace_bytes": [_I, ctypes.POINTER(_Z)],

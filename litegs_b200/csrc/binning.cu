@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) allocate_size_kernel(
     if (g.visible) {
         left_up[o2] = lgs_f2i_rz(ceilf(g.bbox_min[0])); left_up[o2 + N] = lgs_f2i_rz(ceilf(g.bbox_min[1]));
         right_down[o2] = lgs_f2i_rz(floorf(g.bbox_max[0])); right_down[o2 + N] = lgs_f2i_rz(floorf(g.bbox_max[1]));
-        alloc[(size_t)b * N + i] = lgs_process_tiles<TH, TW, false>(g, gx, i, 0, 0, nullptr, nullptr);
+        alloc[(size_t)b * N + i] = lgs_process_tiles<TH, TW, false>(g, gx, i, 0, 0, (int*)nullptr, (int*)nullptr);
     } else {
         left_up[o2] = -1; left_up[o2 + N] = -1; right_down[o2] = -1; right_down[o2 + N] = -1;
         alloc[(size_t)b * N + i] = 0;
@@ -146,39 +146,78 @@ __global__ void fill_int_kernel(int* __restrict__ p, int v, size_t n)
     if (i < n) p[i] = v;
 }
 
-__global__ void tile_range_kernel(const int* __restrict__ keys, int L, int max_tile, int fix_last, int* __restrict__ range)
+// KeyT = int (op-level table) or unsigned short (fused pipeline when tiles+1 < 65536).  Each thread owns VEC consecutive
+// keys, fetched with one vector load, plus the first key of the next group.
+template <typename KeyT, int VEC>
+__global__ void __launch_bounds__(256) tile_range_kernel(const KeyT* __restrict__ keys, int L, int max_tile, int fix_last,
+                                                         int* __restrict__ range)
 {
-    int j = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-    const int* k = keys + (size_t)b * L;
+    const int b = blockIdx.y;
+    const KeyT* k = keys + (size_t)b * L;
     int* r = range + (size_t)b * (max_tile + 2);
-    if (j >= L) return;
-    int cur = k[j];
-    if (j == 0) r[cur] = 0;
-    if (j == L - 1) {
-        r[max_tile + 1] = L;
-        if (fix_last && cur + 1 <= max_tile + 1) r[cur + 1] = L;
+    const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (j0 >= L) return;
+    int key[VEC + 1];
+    if (VEC > 1 && j0 + VEC <= L) {
+        struct __align__(sizeof(KeyT) * VEC) Pack { KeyT v[VEC]; };
+        Pack pk = *reinterpret_cast<const Pack*>(k + j0);
+#pragma unroll
+        for (int i = 0; i < VEC; i++) key[i] = (int)pk.v[i];
     } else {
-        int nxt = k[j + 1];
-        if (cur != nxt) {
-            if (cur + 1 < nxt) r[cur + 1] = j + 1;
-            r[nxt] = j + 1;
+#pragma unroll
+        for (int i = 0; i < VEC; i++) key[i] = (j0 + i < L) ? (int)k[j0 + i] : -1;
+    }
+    key[VEC] = (j0 + VEC < L) ? (int)k[j0 + VEC] : -1;
+    if (j0 == 0) r[key[0]] = 0;
+#pragma unroll
+    for (int i = 0; i < VEC; i++) {
+        const int j = j0 + i;
+        if (j >= L) break;
+        const int cur = key[i];
+        if (j == L - 1) {
+            r[max_tile + 1] = L;
+            if (fix_last && cur + 1 <= max_tile + 1) r[cur + 1] = L;
+        } else {
+            const int nxt = key[i + 1];
+            if (cur != nxt) {
+                if (cur + 1 < nxt) r[cur + 1] = j + 1;
+                r[nxt] = j + 1;
+            }
         }
     }
+}
+
+template <typename KeyT>
+static int tile_range_launch(const KeyT* keys, int V, int L, int max_tile, int fix_last, int* range, cudaStream_t st)
+{
+    size_t n = (size_t)V * (max_tile + 2);
+    fill_int_kernel<<<lgs_cdiv((long long)n, 256), 256, 0, st>>>(range, -1, n);
+    LGS_CHECK_LAUNCH("fill_int_kernel");
+    if (L > 0) {
+        constexpr int VEC = 16 / sizeof(KeyT);             // one 16-byte load per thread
+        const bool aligned = (((uintptr_t)keys) % 16 == 0) && (V == 1 || ((size_t)L * sizeof(KeyT)) % 16 == 0);
+        if (aligned)
+            tile_range_kernel<KeyT, VEC><<<dim3(lgs_cdiv(lgs_cdiv(L, VEC), 256), V), 256, 0, st>>>(keys, L, max_tile, fix_last, range);
+        else
+            tile_range_kernel<KeyT, 1><<<dim3(lgs_cdiv(L, 256), V), 256, 0, st>>>(keys, L, max_tile, fix_last, range);
+        LGS_CHECK_LAUNCH("tile_range_kernel");
+    }
+    return LGS_OK;
 }
 
 extern "C" int lgs_tile_range(const int* table_tile_id, int V, int table_length, int max_tile_id, int fix_last, int* tile_range,
                               void* stream)
 {
     LGS_REQUIRE(V >= 1 && table_length >= 0 && max_tile_id >= 0, "tileRange: bad sizes V=%d L=%d max_tile=%d", V, table_length, max_tile_id);
-    cudaStream_t st = (cudaStream_t)stream;
-    size_t n = (size_t)V * (max_tile_id + 2);
-    fill_int_kernel<<<lgs_cdiv((long long)n, 256), 256, 0, st>>>(tile_range, -1, n);
-    LGS_CHECK_LAUNCH("fill_int_kernel");
-    if (table_length > 0) {
-        tile_range_kernel<<<dim3(lgs_cdiv(table_length, 512), V), 512, 0, st>>>(table_tile_id, table_length, max_tile_id, fix_last, tile_range);
-        LGS_CHECK_LAUNCH("tile_range_kernel");
-    }
-    return LGS_OK;
+    return tile_range_launch<int>(table_tile_id, V, table_length, max_tile_id, fix_last, tile_range, (cudaStream_t)stream);
+}
+
+extern "C" int lgs_tile_range_u16(const unsigned short* table_tile_id, int V, int table_length, int max_tile_id, int fix_last,
+                                  int* tile_range, void* stream)
+{
+    LGS_REQUIRE(V >= 1 && table_length >= 0 && max_tile_id >= 0 && max_tile_id < 65535, "tileRange(u16): bad sizes V=%d L=%d max_tile=%d", V,
+                table_length, max_tile_id);
+    return tile_range_launch<unsigned short>(table_tile_id, V, table_length, max_tile_id, fix_last, tile_range, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -205,6 +244,32 @@ extern "C" int lgs_sort_pairs_u32(const unsigned* keys_in, unsigned* keys_out, c
     }
     LGS_CUDA(cub::DeviceRadixSort::SortPairs<unsigned, unsigned>(ws, need, keys_in, keys_out, vals_in, vals_out, n, begin_bit, end_bit,
                                                                  (cudaStream_t)stream));
+    return LGS_OK;
+}
+
+// 16-bit tile keys (tiles+1 < 65536, i.e. anything up to 4K at 8x16): 6 instead of 8 bytes per pair and pass
+extern "C" int lgs_sort_pairs_u16_workspace_bytes(int n, size_t* bytes)
+{
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs<unsigned short, unsigned>(nullptr, tmp, nullptr, nullptr, nullptr, nullptr, n, 0, 16);
+    *bytes = tmp + 256;
+    return LGS_OK;
+}
+
+extern "C" int lgs_sort_pairs_u16(const unsigned short* keys_in, unsigned short* keys_out, const unsigned* vals_in, unsigned* vals_out,
+                                  int n, int begin_bit, int end_bit, void* workspace, size_t workspace_bytes, void* stream)
+{
+    if (n <= 0) return LGS_OK;
+    LGS_REQUIRE(end_bit <= 16, "sort_pairs_u16: end_bit %d > 16", end_bit);
+    size_t need = 0;
+    cub::DeviceRadixSort::SortPairs<unsigned short, unsigned>(nullptr, need, nullptr, nullptr, nullptr, nullptr, n, begin_bit, end_bit);
+    void* ws = (void*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    if (workspace == nullptr || workspace_bytes < need + 256) {
+        lgs_set_error("sort_pairs_u16: workspace of %zu bytes needed, %zu given", need + 256, workspace_bytes);
+        return LGS_ERR_WORKSPACE;
+    }
+    LGS_CUDA(cub::DeviceRadixSort::SortPairs<unsigned short, unsigned>(ws, need, keys_in, keys_out, vals_in, vals_out, n, begin_bit, end_bit,
+                                                                       (cudaStream_t)stream));
     return LGS_OK;
 }
 

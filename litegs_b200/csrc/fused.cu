@@ -139,7 +139,7 @@ __global__ void project_forward_kernel(
         const float ndcx = t.h[0] * t.iw, ndcy = t.h[1] * t.iw, ndcz = t.h[2] * t.iw;
         SplatGeom g;
         lgs_splat_setup<TH, TW>(ndcx, ndcy, t.v[2], t.inv[0], t.inv[1], t.inv[2], t.o, H, W, gx, gy, true, g);
-        if (g.visible) count = lgs_process_tiles<TH, TW, false>(g, gx, 0, 0, 0, nullptr, nullptr);
+        if (g.visible) count = lgs_process_tiles<TH, TW, false>(g, gx, 0, 0, 0, (int*)nullptr, (int*)nullptr);
         if (count > 0) key = __float_as_uint(t.v[2]);       // v.z > 0.2 here: positive floats order as unsigned
         r.px = __fsub_rn(__fmul_rn(__fmul_rn(__fadd_rn(ndcx, 1.0f), 0.5f), (float)W), 0.5f);   // GR/raster.cu:347-348
         r.py = __fsub_rn(__fmul_rn(__fmul_rn(__fadd_rn(ndcy, 1.0f), 0.5f), (float)H), 0.5f);
@@ -180,10 +180,10 @@ extern "C" int lgs_project_forward(int sh_degree, const int64_t* visible_chunk_i
 }
 
 // (tile+1, splat) emission in depth order from the packed record.    replaces GR/binning.cu:33-110
-template <int TH, int TW>
+template <int TH, int TW, typename KeyT>
 __global__ void __launch_bounds__(256) emit_pairs_rec_kernel(const SplatRec* __restrict__ recs, const int* __restrict__ offset,
                                                              const unsigned* __restrict__ order, int n, int cap, int H, int W,
-                                                             int gx, int gy, int* __restrict__ keys, int* __restrict__ vals)
+                                                             int gx, int gy, KeyT* __restrict__ keys, int* __restrict__ vals)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(256) emit_pairs_rec_kernel(const SplatRec* __r
     const SplatRec r = recs[i];
     SplatGeom g;
     lgs_splat_setup<TH, TW>(r.pad0, r.pad1, 1.0f, r.A, r.B, r.C, r.o, H, W, gx, gy, false, g);
-    if (g.visible) lgs_process_tiles<TH, TW, true>(g, gx, i, off, cap, keys, vals);
+    if (g.visible) lgs_process_tiles<TH, TW, true, KeyT>(g, gx, i, off, cap, keys, vals);
 }
 
 extern "C" int lgs_emit_pairs(const float* packed_params, const int* offset, const unsigned* order, int n, int cap, int img_h,
@@ -205,9 +205,25 @@ extern "C" int lgs_emit_pairs(const float* packed_params, const int* offset, con
     int gx = (img_w + tile_w - 1) / tile_w, gy = (img_h + tile_h - 1) / tile_h;
     cudaStream_t st = (cudaStream_t)stream;
     LGS_DISPATCH_TILE(tile_h, tile_w,
-        emit_pairs_rec_kernel<TH, TW><<<lgs_cdiv(n, 256), 256, 0, st>>>((const SplatRec*)packed_params, offset, order, n, cap, img_h,
-                                                                      img_w, gx, gy, keys, vals);)
+        emit_pairs_rec_kernel<TH, TW, int><<<lgs_cdiv(n, 256), 256, 0, st>>>((const SplatRec*)packed_params, offset, order, n, cap, img_h,
+                                                                           img_w, gx, gy, keys, vals);)
     LGS_CHECK_LAUNCH("emit_pairs_rec_kernel");
+    return LGS_OK;
+}
+
+// same with 16-bit tile keys (requires tiles + 1 < 65536)
+extern "C" int lgs_emit_pairs_u16(const float* packed_params, const int* offset, const unsigned* order, int n, int cap, int img_h,
+                                  int img_w, int tile_h, int tile_w, unsigned short* keys, int* vals, void* stream)
+{
+    LGS_REQUIRE(lgs_tile_ok(tile_h, tile_w), "emit_pairs_u16: tile %dx%d not one of 8x16, 12x16, 16x16, 8x8", tile_h, tile_w);
+    if (n <= 0 || cap <= 0) return LGS_OK;
+    int gx = (img_w + tile_w - 1) / tile_w, gy = (img_h + tile_h - 1) / tile_h;
+    LGS_REQUIRE(gx * gy + 1 < 65536, "emit_pairs_u16: %d tiles do not fit 16-bit keys", gx * gy);
+    cudaStream_t st = (cudaStream_t)stream;
+    LGS_DISPATCH_TILE(tile_h, tile_w,
+        emit_pairs_rec_kernel<TH, TW, unsigned short><<<lgs_cdiv(n, 256), 256, 0, st>>>((const SplatRec*)packed_params, offset, order, n, cap,
+                                                                                      img_h, img_w, gx, gy, keys, vals);)
+    LGS_CHECK_LAUNCH("emit_pairs_rec_kernel<u16>");
     return LGS_OK;
 }
 

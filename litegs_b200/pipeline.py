@@ -129,17 +129,21 @@ def render_view_forward(params: dict, cluster_origin: torch.Tensor, cluster_exte
             ws2 = ws if nb2 <= nb else torch.empty(nb2, dtype=_U8, device=dev)
             offsets = dkey_s     # the sorted keys are dead now: reuse their storage for the scan
             _lib.call("lgs_scan_gathered", _ptr(tcount), _ptr(order), Nv, _ptr(offsets), _ptr(ws2), ctypes.c_size_t(max(nb, nb2)), st)
-            keys = torch.empty(D, dtype=_I32, device=dev)
-            vals = torch.empty(D, dtype=_I32, device=dev)
-            _lib.call("lgs_emit_pairs", _ptr(packed), _ptr(offsets), _ptr(order), Nv, D, H, W, th, tw, _ptr(keys), _ptr(vals), st)
             bits = ntile.bit_length()          # floor(log2(tiles)) + 1, GR/binning.cu:199-202
-            nb3 = _query_bytes("lgs_sort_pairs_u32_workspace_bytes", _round_up(D, 1 << 18))
+            u16 = (ntile + 1) < 65536          # 16-bit tile keys whenever they fit (up to 4K at 8x16)
+            kdt = torch.int16 if u16 else _I32
+            sfx = "_u16" if u16 else "_u32"
+            keys = torch.empty(D, dtype=kdt, device=dev)
+            vals = torch.empty(D, dtype=_I32, device=dev)
+            _lib.call("lgs_emit_pairs_u16" if u16 else "lgs_emit_pairs", _ptr(packed), _ptr(offsets), _ptr(order), Nv, D, H, W, th, tw,
+                      _ptr(keys), _ptr(vals), st)
+            nb3 = _query_bytes(f"lgs_sort_pairs{sfx}_workspace_bytes", _round_up(D, 1 << 18))
             ws3 = ws if nb3 <= nb else torch.empty(nb3, dtype=_U8, device=dev)
-            keys_s = torch.empty((1, D), dtype=_I32, device=dev)
+            keys_s = torch.empty((1, D), dtype=kdt, device=dev)
             sorted_pid = torch.empty((1, D), dtype=_I32, device=dev)
-            _lib.call("lgs_sort_pairs_u32", _ptr(keys), _ptr(keys_s), _ptr(vals), _ptr(sorted_pid), D, 0, bits, _ptr(ws3),
+            _lib.call(f"lgs_sort_pairs{sfx}", _ptr(keys), _ptr(keys_s), _ptr(vals), _ptr(sorted_pid), D, 0, bits, _ptr(ws3),
                       ctypes.c_size_t(max(nb, nb3)), st)
-            _lib.call("lgs_tile_range", _ptr(keys_s), 1, D, ntile, 1, _ptr(ranges), st)
+            _lib.call("lgs_tile_range_u16" if u16 else "lgs_tile_range", _ptr(keys_s), 1, D, ntile, 1, _ptr(ranges), st)
         else:
             sorted_pid = torch.zeros((1, 1), dtype=_I32, device=dev)
             _lib.call("lgs_tile_range", None, 1, 0, ntile, 1, _ptr(ranges), st)
