@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--gaussians", type=int, default=1_000_000)
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--tile", default="16x16", help="8x16 (reference default) | 12x16 | 16x16 | 8x8")
+    ap.add_argument("--tile", default="8x16", help="8x16 (reference default) | 12x16 | 16x16 | 8x8")
     ap.add_argument("--sh-degree", type=int, default=3)
     ap.add_argument("--views-per-rank", type=int, default=8)
     ap.add_argument("--n-views", type=int, default=64, help="size of the camera lattice the step's views are drawn from")
@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--level", default="B", choices=["A", "B"], help="B = fused render_view (default), A = op-by-op surface")
     ap.add_argument("--staging", default=None, choices=[None, "bulk", "cpasync"])
-    ap.add_argument("--streams", type=int, default=2, help="CUDA streams the views of a step alternate over (1 = serial)")
+    ap.add_argument("--streams", type=int, default=3, help="CUDA streams the views of a step alternate over (1 = serial)")
     return ap.parse_args()
 
 
@@ -165,8 +165,11 @@ def stage_bytes(stats, S, K):
         "lgs_sort_pairs_u32(depth)": (4 + 4 * 16) * Nv,
         "lgs_scan_gathered": 12 * Nv,
         "lgs_emit_pairs": 60 * Nv + 8 * D,
+        "lgs_emit_pairs_u16": 60 * Nv + 6 * D,
         "lgs_sort_pairs_u32(tile)": (4 + bits_passes * 16) * D,
+        "lgs_sort_pairs_u16(tile)": (2 + bits_passes * 12) * D,
         "lgs_tile_range": 4 * D,
+        "lgs_tile_range_u16": 2 * D,
         "lgs_rasterize_forward_packed": 4 * D + 48 * Nvis + 18 * P,
         "lgs_rasterize_backward": 48 * Nmax + 4 * D + 48 * Nvis + 30 * P + 36 * Nvis,
         "lgs_project_backward": 48 * Nv + 44 * Nv + par * Nv,
@@ -455,14 +458,18 @@ def run_ours(args, rank, world, local_rank):
     sort_calls = summ.get("lgs_sort_pairs_u32")
     for name, (tot, n) in summ.items():
         stages[name] = {"ms_per_view": tot / n_views_rank, "launches_per_view": n / n_views_rank}
-    # the two radix sorts share an entry point: split by call parity (depth sort first, tile sort second)
+    # the depth sort and (with 32-bit tile keys) the tile sort share an entry point: split by call parity
     if "lgs_sort_pairs_u32" in timer.rec:
         evs = timer.rec["lgs_sort_pairs_u32"]
-        d = sum(a.elapsed_time(b) for a, b in evs[0::2]) / n_views_rank
-        tl = sum(a.elapsed_time(b) for a, b in evs[1::2]) / n_views_rank
-        stages["lgs_sort_pairs_u32(depth)"] = {"ms_per_view": d, "launches_per_view": 1.0}
-        stages["lgs_sort_pairs_u32(tile)"] = {"ms_per_view": tl, "launches_per_view": 1.0}
-        del stages["lgs_sort_pairs_u32"]
+        if "lgs_sort_pairs_u16" in timer.rec:            # 16-bit tile keys: every u32 sort is the depth sort
+            stages["lgs_sort_pairs_u32(depth)"] = stages.pop("lgs_sort_pairs_u32")
+            stages["lgs_sort_pairs_u16(tile)"] = stages.pop("lgs_sort_pairs_u16")
+        else:
+            d = sum(a.elapsed_time(b) for a, b in evs[0::2]) / n_views_rank
+            tl = sum(a.elapsed_time(b) for a, b in evs[1::2]) / n_views_rank
+            stages["lgs_sort_pairs_u32(depth)"] = {"ms_per_view": d, "launches_per_view": 1.0}
+            stages["lgs_sort_pairs_u32(tile)"] = {"ms_per_view": tl, "launches_per_view": 1.0}
+            del stages["lgs_sort_pairs_u32"]
     for name, s_ in stages.items():
         b = bytes_per.get(name)
         if b is not None and s_["ms_per_view"] > 0:
@@ -482,12 +489,13 @@ def run_ours(args, rank, world, local_rank):
             "frac": path_bytes / (ms_view / 1000.0) / 1e9 / peak_gbs,
             "survey_formula_bytes": int(survey_bytes), "survey_formula_frac": survey_bytes / (ms_view / 1000.0) / 1e9 / peak_gbs,
             "ms_per_view": ms_view, "ms_per_view_single_stream": ms_view_serial}
-    hand_written = ("lgs_frustum_culling_aabb", "lgs_project_forward", "lgs_emit_pairs", "lgs_tile_range", "lgs_rasterize_forward_packed",
-                    "lgs_rasterize_backward", "lgs_project_backward", "lgs_sparse_chunk_op", "lgs_pack_params")
+    hand_written = ("lgs_frustum_culling_aabb", "lgs_project_forward", "lgs_emit_pairs", "lgs_emit_pairs_u16", "lgs_tile_range",
+                    "lgs_tile_range_u16", "lgs_rasterize_forward_packed", "lgs_rasterize_backward", "lgs_project_backward",
+                    "lgs_sparse_chunk_op", "lgs_pack_params")
     gpu_launches = 0
     for name, (tot, n) in summ.items():
         if name in hand_written:
-            mult = {"lgs_tile_range": 2}.get(name, 1)       # fill + range kernels
+            mult = {"lgs_tile_range": 2, "lgs_tile_range_u16": 2}.get(name, 1)       # fill + range kernels
             gpu_launches += n * mult
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
