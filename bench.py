@@ -183,6 +183,8 @@ def stage_bytes(stats, S, K):
 
 def cpu_views_per_s(args, scene_np, n_views, weights_seed=1):
     import oracle
+    # all host threads (torchrun exports OMP_NUM_THREADS=1 to its workers, which would make this a 1-core run)
+    oracle.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     P = {k: scene_np[k] for k in PARAM_KEYS}
     aabb = (scene_np["cluster_origin"], scene_np["cluster_extend"])
     th, tw = [int(x) for x in args.tile.split("x")]
@@ -223,7 +225,7 @@ def run_reference(args, rank):
         line["ref_cuda"] = ref_cuda_views_per_s(args, scene_np)
     except Exception as e:  # pragma: no cover
         line["ref_cuda"] = {"unavailable": str(e)[:200]}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 def ref_cuda_views_per_s(args, scene_np, iters=20):
@@ -517,11 +519,28 @@ def run_ours(args, rank, world, local_rank):
                                     "sample": f"{args.cpu_views} full-size views of the same workload (oracle/, C + OpenMP), {dt:.1f} s"}
         except Exception as e:
             line["cpu_baseline"] = {"unavailable": str(e)[:200]}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit_line(obj):
+    """The one JSON line of this run, on the real stdout."""
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
 
 
 def main():
+    global _REAL_STDOUT
     args = parse()
+    # stdout carries exactly one JSON line: everything else (NCCL's version banner, library chatter) goes to stderr
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

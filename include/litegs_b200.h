@@ -156,20 +156,24 @@ int lgs_pack_params(const float* ndc, const float* cov2d_inv, const float* color
 /* rasterize_forward(_packed), GR/raster.cu:161-332,386-586 (GR/raster.h:3-33).  Images are padded to
  * whole tiles: img f32[V,3,Hp,Wp], transmittance f32[V,1,Hp,Wp], last_contributor i16[V,1,Hp,Wp];
  * fragment_count i32[V,1,N] / fragment_weight f32[V,1,N] are accumulated when enable_statistic (caller
- * zeroes them).  specific_tiles i32[V,n_specific] (1-based tile ids, 0 = skip) or NULL. */
+ * zeroes them).  specific_tiles i32[V,n_specific] (1-based tile ids, 0 = skip) or NULL.  clamp_zero=0 writes
+ * min(c,1) as the reference kernel does; 1 writes clamp(c,0,1), i.e. also the clamp render() applies in Python
+ * (render/__init__.py:87) -- then pass the image back to lgs_rasterize_backward as `clamped_img`. */
 int lgs_rasterize_forward_packed(const int* sorted_points, const int* start_index, const float* packed_params,
                                  const int* specific_tiles, int n_specific, int V, int N, int cap, int img_h, int img_w,
-                                 int tile_h, int tile_w, int enable_statistic, float* img, float* transmittance,
-                                 short* last_contributor, int* fragment_count, float* fragment_weight, void* stream);
+                                 int tile_h, int tile_w, int enable_statistic, int clamp_zero, float* img,
+                                 float* transmittance, short* last_contributor, int* fragment_count,
+                                 float* fragment_weight, void* stream);
 
 /* rasterize_backward, GR/raster.cu:599-886,917-1037 (GR/raster.h:35-50).  packed_grad f32[V,N,12] is
- * scratch (zeroed here); d_trans_img and grad_inv_scaler (DEVICE f32[1]) may be NULL.  Outputs d_ndc
+ * scratch (zeroed here); d_trans_img, clamped_img (the forward's clamp_zero=1 output: blocks the gradient where a
+ * colour was clamped up to 0) and grad_inv_scaler (DEVICE f32[1]) may be NULL.  Outputs d_ndc
  * f32[V,4,N], d_cov2d_inv f32[V,2,2,N], d_color f32[V,3,N], d_opacity f32[1,N] (view 0 only, as the
  * reference), err_sum/err_square_sum f32[V,1,N].  Pass d_ndc=NULL to skip the unpack (fused path). */
 int lgs_rasterize_backward(const int* sorted_points, const int* start_index, const float* packed_params,
                            const int* specific_tiles, int n_specific, const float* final_transmittance,
                            const short* last_contributor, const float* d_img, const float* d_trans_img,
-                           const float* grad_inv_scaler, int V, int N, int cap, int img_h, int img_w, int tile_h,
+                           const float* clamped_img, const float* grad_inv_scaler, int V, int N, int cap, int img_h, int img_w, int tile_h,
                            int tile_w, int enable_statistic, float* packed_grad, float* d_ndc, float* d_cov2d_inv,
                            float* d_color, float* d_opacity, float* err_sum, float* err_square_sum, void* stream);
 

@@ -43,8 +43,8 @@ SIGNATURES = {
     "lgs_scan_gathered_workspace_bytes": [_I, ctypes.POINTER(_Z)],
     "lgs_scan_gathered": [_P, _P, _I, _P, _P, _Z, _P],
     "lgs_pack_params": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
-    "lgs_rasterize_forward_packed": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
-    "lgs_rasterize_backward": [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I,
+    "lgs_rasterize_forward_packed": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    "lgs_rasterize_backward": [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I,
                                _P, _P, _P, _P, _P, _P, _P, _P],
     "lgs_set_staging": [_I],
     "lgs_set_warps_per_block": [_I],

@@ -190,7 +190,8 @@ template <int TH, int TW, bool STAT, bool BULK>
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_forward_kernel(
     const int* __restrict__ sorted, const int* __restrict__ start_index, const SplatRec* __restrict__ recs,
     const int* __restrict__ tiles, int n_sel, float* __restrict__ img, float* __restrict__ Tout, short* __restrict__ last,
-    int* __restrict__ frag_count, float* __restrict__ frag_weight, int gx, int ntile, int cap, int N, int Hp, int Wp)
+    int* __restrict__ frag_count, float* __restrict__ frag_weight, int gx, int ntile, int cap, int N, int Hp, int Wp,
+    int clamp_zero)
 {
     constexpr int PPT = TH * TW / 32;
     __shared__ __align__(128) SplatRec s_rec[WARPS_PER_BLOCK][2][32];
@@ -293,9 +294,12 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_forward_kernel(
 #pragma unroll
     for (int j = 0; j < PPT; j++) {
         const size_t po = (size_t)(y0 + j) * Wp + x;
-        img[((size_t)b * 3 + 0) * plane + po] = fminf(Cr[j], 1.0f);
-        img[((size_t)b * 3 + 1) * plane + po] = fminf(Cg[j], 1.0f);
-        img[((size_t)b * 3 + 2) * plane + po] = fminf(Cb[j], 1.0f);
+        // min(c,1) as the reference kernel (GR/raster.cu:313); clamp_zero additionally applies the lower half of the
+        // clamp(0,1) that render() performs in Python (render/__init__.py:87), saving an elementwise pass.
+        const float lo = clamp_zero ? 0.0f : -3.4028234663852886e38f;
+        img[((size_t)b * 3 + 0) * plane + po] = fmaxf(fminf(Cr[j], 1.0f), lo);
+        img[((size_t)b * 3 + 1) * plane + po] = fmaxf(fminf(Cg[j], 1.0f), lo);
+        img[((size_t)b * 3 + 2) * plane + po] = fmaxf(fminf(Cb[j], 1.0f), lo);
         Tout[(size_t)b * plane + po] = Ts[j] * KS;
         last[(size_t)b * plane + po] = (short)(int)nf[j];
     }
@@ -329,8 +333,8 @@ template <int TH, int TW, bool STAT, bool TRANS, bool BULK>
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_kernel(
     const int* __restrict__ sorted, const int* __restrict__ start_index, const SplatRec* __restrict__ recs,
     const int* __restrict__ tiles, int n_sel, const float* __restrict__ Tfinal, const short* __restrict__ last,
-    const float* __restrict__ d_img, const float* __restrict__ d_trans, float* __restrict__ grad, int gx, int ntile, int cap,
-    int N, int Hp, int Wp)
+    const float* __restrict__ d_img, const float* __restrict__ d_trans, const float* __restrict__ clamped_img,
+    float* __restrict__ grad, int gx, int ntile, int cap, int N, int Hp, int Wp)
 {
     constexpr int PPT = TH * TW / 32;
     __shared__ __align__(128) SplatRec s_rec[WARPS_PER_BLOCK][2][32];
@@ -366,6 +370,13 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_kernel(
         g0[j] = d_img[((size_t)b * 3 + 0) * plane + po];
         g1[j] = d_img[((size_t)b * 3 + 1) * plane + po];
         g2[j] = d_img[((size_t)b * 3 + 2) * plane + po];
+        if (clamped_img != nullptr) {
+            // backward of the fused clamp(0,1): the gradient is blocked where the colour was clamped up to 0
+            // (min(c,1) already lets it through at 1, exactly like torch.clamp's backward on the reference path)
+            if (!(clamped_img[((size_t)b * 3 + 0) * plane + po] > 0.0f)) g0[j] = 0.0f;
+            if (!(clamped_img[((size_t)b * 3 + 1) * plane + po] > 0.0f)) g1[j] = 0.0f;
+            if (!(clamped_img[((size_t)b * 3 + 2) * plane + po] > 0.0f)) g2[j] = 0.0f;
+        }
         gt[j] = TRANS ? d_trans[(size_t)b * plane + po] * T[j] : 0.0f;   // dL/dT_final * T_final
         S[j] = 0.0f;
         nl[j] = (int)last[(size_t)b * plane + po];
@@ -527,8 +538,9 @@ extern "C" int lgs_pack_params(const float* ndc, const float* cov2d_inv, const f
 // (must be zero-initialised by the caller when enable_statistic).
 extern "C" int lgs_rasterize_forward_packed(const int* sorted_points, const int* start_index, const float* packed_params,
                                             const int* specific_tiles, int n_specific, int V, int N, int cap, int img_h, int img_w,
-                                            int tile_h, int tile_w, int enable_statistic, float* img, float* transmittance,
-                                            short* last_contributor, int* fragment_count, float* fragment_weight, void* stream)
+                                            int tile_h, int tile_w, int enable_statistic, int clamp_zero, float* img,
+                                            float* transmittance, short* last_contributor, int* fragment_count,
+                                            float* fragment_weight, void* stream)
 {
     LGS_REQUIRE(lgs_tile_ok(tile_h, tile_w), "rasterize_forward: tile %dx%d not one of 8x16, 12x16, 16x16, 8x8", tile_h, tile_w);
     LGS_REQUIRE(V >= 1 && img_h > 0 && img_w > 0, "rasterize_forward: bad sizes V=%d H=%d W=%d", V, img_h, img_w);
@@ -542,7 +554,7 @@ extern "C" int lgs_rasterize_forward_packed(const int* sorted_points, const int*
     const SplatRec* recs = (const SplatRec*)packed_params;
     const bool bulk = use_bulk();
 #define FWD(S, B) raster_forward_kernel<TH, TW, S, B><<<grid, block, 0, st>>>(sorted_points, start_index, recs, specific_tiles, n_specific, \
-        img, transmittance, last_contributor, fragment_count, fragment_weight, gx, ntile, cap, N, Hp, Wp)
+        img, transmittance, last_contributor, fragment_count, fragment_weight, gx, ntile, cap, N, Hp, Wp, clamp_zero)
     LGS_DISPATCH_TILE(tile_h, tile_w,
         if (enable_statistic) { if (bulk) FWD(true, true); else FWD(true, false); }
         else { if (bulk) FWD(false, true); else FWD(false, false); })
@@ -555,7 +567,8 @@ extern "C" int lgs_rasterize_forward_packed(const int* sorted_points, const int*
 extern "C" int lgs_rasterize_backward(const int* sorted_points, const int* start_index, const float* packed_params,
                                       const int* specific_tiles, int n_specific, const float* final_transmittance,
                                       const short* last_contributor, const float* d_img, const float* d_trans_img,
-                                      const float* grad_inv_scaler, int V, int N, int cap, int img_h, int img_w, int tile_h,
+                                      const float* clamped_img, const float* grad_inv_scaler, int V, int N, int cap, int img_h,
+                                      int img_w, int tile_h,
                                       int tile_w, int enable_statistic, float* packed_grad, float* d_ndc, float* d_cov2d_inv,
                                       float* d_color, float* d_opacity, float* err_sum, float* err_square_sum, void* stream)
 {
@@ -574,7 +587,7 @@ extern "C" int lgs_rasterize_backward(const int* sorted_points, const int* start
         const bool bulk = use_bulk();
         const bool trans = d_trans_img != nullptr;
 #define BWD(S, T, B) raster_backward_kernel<TH, TW, S, T, B><<<grid, block, 0, st>>>(sorted_points, start_index, recs, specific_tiles, \
-        n_specific, final_transmittance, last_contributor, d_img, d_trans_img, packed_grad, gx, ntile, cap, N, Hp, Wp)
+        n_specific, final_transmittance, last_contributor, d_img, d_trans_img, clamped_img, packed_grad, gx, ntile, cap, N, Hp, Wp)
         LGS_DISPATCH_TILE(tile_h, tile_w,
             if (enable_statistic) { if (trans) { if (bulk) BWD(true, true, true); else BWD(true, true, false); }
                                     else { if (bulk) BWD(true, false, true); else BWD(true, false, false); } }

@@ -75,7 +75,7 @@ class _Pinned:
 
 def render_view_forward(params: dict, cluster_origin: torch.Tensor, cluster_extend: torch.Tensor, frustumplane: torch.Tensor,
                         view_matrix: torch.Tensor, proj_matrix: torch.Tensor, sh_degree: int, hw: tuple, tile: tuple,
-                        enable_statistic: bool = False, specific_tiles: Optional[torch.Tensor] = None):
+                        enable_statistic: bool = False, specific_tiles: Optional[torch.Tensor] = None, clamp_zero: bool = False):
     """Forward of one view.  params: xyz[3,C,S] scale[3,C,S] rot[4,C,S] sh_0[1,3,C,S] sh_rest[R,3,C,S]
     opacity[1,C,S] (raw, clustered; float32 CUDA, contiguous).  Returns (img f32[1,3,Hp,Wp] padded to whole
     tiles, ViewState, (fragment_count, fragment_weight) or None)."""
@@ -162,8 +162,8 @@ def render_view_forward(params: dict, cluster_origin: torch.Tensor, cluster_exte
             fw = torch.zeros((1, 1, Nmax), dtype=_F32, device=dev)
             stats = (fc, fw)
         _lib.call("lgs_rasterize_forward_packed", _ptr(sorted_pid), _ptr(ranges), _ptr(packed), _ptr(specific_tiles), n_sel, 1,
-                  Nmax, sorted_pid.shape[1], H, W, th, tw, int(bool(enable_statistic)), _ptr(img), _ptr(T), _ptr(last), _ptr(fc),
-                  _ptr(fw), st)
+                  Nmax, sorted_pid.shape[1], H, W, th, tw, int(bool(enable_statistic)), int(bool(clamp_zero)), _ptr(img), _ptr(T),
+                  _ptr(last), _ptr(fc), _ptr(fw), st)
     state = ViewState(sh_degree=int(sh_degree), hw=(H, W), tile=(th, tw), n_chunks_visible=nvis, n_pairs=D, chunk_ids=ids,
                       counters=counters, view=view_matrix, proj=proj_matrix, packed=packed, tile_count=tcount,
                       sorted_pid=sorted_pid, ranges=ranges, T=T, last=last)
@@ -172,7 +172,7 @@ def render_view_forward(params: dict, cluster_origin: torch.Tensor, cluster_exte
 
 def render_view_backward(params: dict, state: ViewState, d_img: torch.Tensor, d_trans: Optional[torch.Tensor] = None,
                          enable_statistic: bool = False, specific_tiles: Optional[torch.Tensor] = None,
-                         accumulate_into: Optional[dict] = None):
+                         accumulate_into: Optional[dict] = None, clamped_img: Optional[torch.Tensor] = None):
     """Backward of one view: d_img f32[1,3,Hp,Wp] (padded) -> compacted parameter gradients
     (xyz[3,A,S], scale[3,A,S], rot[4,A,S], sh_0[1,3,A,S], sh_rest[R,3,A,S], opacity[1,A,S]) with
     A = state.n_chunks_visible, plus packed_grad (whose slot 9 carries the statistics term).
@@ -198,7 +198,8 @@ def render_view_backward(params: dict, state: ViewState, d_img: torch.Tensor, d_
         pg = torch.empty((1, Nmax, 12), dtype=_F32, device=dev)
         n_sel = 0 if specific_tiles is None else specific_tiles.shape[1]
         _lib.call("lgs_rasterize_backward", _ptr(state.sorted_pid), _ptr(state.ranges), _ptr(state.packed), _ptr(specific_tiles), n_sel,
-                  _ptr(state.T), _ptr(state.last), _ptr(d_img), _ptr(d_trans), None, 1, Nmax, state.sorted_pid.shape[1], H, W, th, tw,
+                  _ptr(state.T), _ptr(state.last), _ptr(d_img), _ptr(d_trans), _ptr(clamped_img), None, 1, Nmax, state.sorted_pid.shape[1],
+                  H, W, th, tw,
                   int(bool(enable_statistic)), _ptr(pg), None, None, None, None, None, None, st)
         if accumulate_into is not None:
             for k in ("xyz", "scale", "rot", "sh_0", "sh_rest", "opacity"):

@@ -111,27 +111,29 @@ class _RenderViewFn(torch.autograd.Function):
                 view_matrix, proj_matrix, sh_degree, H, W, th, tw, sparse_grad, enable_transmitance, accumulate_into):
         params = dict(xyz=xyz, scale=scale, rot=rot, sh_0=sh_0, sh_rest=sh_rest, opacity=opacity)
         stat = bool(StatisticsHelperInst.bStart)
+        # the kernel writes clamp(c,0,1) directly (render/__init__.py:87 does it as a separate pass) ...
         img, state, stats = pipeline.render_view_forward(params, cluster_origin, cluster_extend, frustumplane, view_matrix,
-                                                         proj_matrix, sh_degree, (H, W), (th, tw), enable_statistic=stat)
+                                                         proj_matrix, sh_degree, (H, W), (th, tw), enable_statistic=stat, clamp_zero=True)
         ctx.state = state
         ctx.stats = stats
         ctx.stat = stat
         ctx.sparse = bool(sparse_grad)
         ctx.trans = bool(enable_transmitance)
         ctx.accumulate_into = accumulate_into
-        ctx.save_for_backward(xyz, scale, rot, sh_0, sh_rest, opacity)
+        ctx.save_for_backward(xyz, scale, rot, sh_0, sh_rest, opacity, img)
         ctx.mark_non_differentiable(state.last)
         return img, state.T, state.last
 
     @staticmethod
     def backward(ctx, g_img, g_T, _g_last):
-        xyz, scale, rot, sh_0, sh_rest, opacity = ctx.saved_tensors
+        xyz, scale, rot, sh_0, sh_rest, opacity, img_out = ctx.saved_tensors
         params = dict(xyz=xyz, scale=scale, rot=rot, sh_0=sh_0, sh_rest=sh_rest, opacity=opacity)
         state = ctx.state
         if g_img is None:
             g_img = torch.zeros((1, 3, *state.T.shape[-2:]), dtype=torch.float32, device=xyz.device)
+        # ... and the backward kernel applies that clamp's gradient mask from the saved image
         grads, pg = pipeline.render_view_backward(params, state, g_img, g_T if ctx.trans else None, enable_statistic=ctx.stat,
-                                                  accumulate_into=ctx.accumulate_into)
+                                                  accumulate_into=ctx.accumulate_into, clamped_img=img_out)
         if ctx.stat and StatisticsHelperInst.on_fragment_weight is not None:
             StatisticsHelperInst.on_fragment_weight(ctx.stats[1], ctx.stats[0])
         if grads is None:          # gradients went straight into the caller's dense buffers
@@ -164,7 +166,7 @@ def render_view(cluster_origin, cluster_extend, frustumplane, view_matrix, proj_
     img, T, last = _RenderViewFn.apply(xyz, scale, rot, sh_0, sh_rest, opacity, cluster_origin, cluster_extend, frustumplane,
                                        view_matrix, proj_matrix, int(actived_sh_degree), H, W, th, tw, pp.sparse_grad,
                                        pp.enable_transmitance, accumulate_into)
-    img = img[..., :H, :W].clamp(0, 1)
+    img = img[..., :H, :W]          # already clamped to [0,1] by the kernel
     trans = T[..., :H, :W] if pp.enable_transmitance else None
     return img, trans, None, None, last
 
