@@ -480,9 +480,18 @@ def run_ours(args, rank, world, local_rank):
     dom = max(stages.items(), key=lambda kv: kv[1]["ms_per_view"])[0] if stages else None
     roofline = None
     if dom is not None and "gbs" in stages[dom]:
+        traffic, issue = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
+            if tj and tj.get("tile") == args.tile:
+                traffic, issue = tj["bytes"], {"issue_slots_busy_pct": tj.get("issue_slots_busy_pct"), "ipc_active": tj.get("ipc_active")}
+        except Exception:
+            pass
         roofline = {"kernel": dom, "bound": "hbm", "achieved": stages[dom]["gbs"], "peak": peak_gbs, "unit": "GB/s",
-                    "frac": stages[dom]["gbs"] / peak_gbs, "traffic": None, "peak_source": peak_src,
-                    "alg_bytes_per_launch": stages[dom]["alg_bytes"], "ms_per_launch": stages[dom]["ms_per_view"]}
+                    "frac": stages[dom]["gbs"] / peak_gbs, "traffic": traffic, "peak_source": peak_src,
+                    "alg_bytes_per_launch": stages[dom]["alg_bytes"], "ms_per_launch": stages[dom]["ms_per_view"],
+                    "note": "this kernel is SM-issue bound, not HBM bound (ncu: DRAM throughput < 2 %); see sm_issue",
+                    "sm_issue": issue}
     path_bytes = sum(v for k, v in bytes_per.items())
     survey_bytes = 748 * stats["Nv"] + 172 * stats["D"] + 48 * stats["P"]
     ms_view = ms / (vpr * args.steps)

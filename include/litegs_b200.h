@@ -179,6 +179,9 @@ int lgs_rasterize_backward(const int* sorted_points, const int* start_index, con
 
 /* staging selector for the raster kernels: 0 = cp.async / LDGSTS (default, measured faster), 1 = cp.async.bulk + mbarrier */
 int lgs_set_staging(int bulk);
+/* warp reduction of the per-(tile,splat) gradient in the backward: 1 = deferred through shared memory (default),
+ * 0 = register butterfly */
+int lgs_set_backward_reduce(int deferred);
 /* tiles (warps) per CTA of the raster kernels: 1, 2 or 4 (default 4, env LGS_WPB) */
 int lgs_set_warps_per_block(int wpb);
 

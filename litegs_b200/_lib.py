@@ -48,6 +48,7 @@ SIGNATURES = {
                                _P, _P, _P, _P, _P, _P, _P, _P],
     "lgs_set_staging": [_I],
     "lgs_set_warps_per_block": [_I],
+    "lgs_set_backward_reduce": [_I],
     "lgs_project_forward": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "lgs_emit_pairs": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "lgs_project_backward": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I,

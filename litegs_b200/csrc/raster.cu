@@ -329,7 +329,15 @@ __device__ __forceinline__ float butterfly8(const float (&v)[8], int lane)
     return z;
 }
 
-template <int TH, int TW, bool STAT, bool TRANS, bool BULK>
+// DEFER selects how the per-(tile,splat) gradient is reduced over the warp's pixels:
+//   false: transposing butterfly in registers (9 + 5 shuffles, ~70 instructions per splat);
+//   true : each lane parks its 9 partials in a per-warp shared-memory matrix [splat*9+value][lane] (9 conflict-free
+//          STS); every RG=3 splats the 27 rows are summed "transposed" -- lane r adds up row r with 8 LDS.128 (rows
+//          padded to 36 floats so a quarter-warp hits 8 distinct bank groups) -- and issues its RED.  ~40 instructions
+//          per splat, no shuffles, no selects on the half-rate ALU pipe.
+#define LGS_RG 3
+#define LGS_ROWF 36
+template <int TH, int TW, bool STAT, bool TRANS, bool BULK, bool DEFER>
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_kernel(
     const int* __restrict__ sorted, const int* __restrict__ start_index, const SplatRec* __restrict__ recs,
     const int* __restrict__ tiles, int n_sel, const float* __restrict__ Tfinal, const short* __restrict__ last,
@@ -337,8 +345,10 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_kernel(
     float* __restrict__ grad, int gx, int ntile, int cap, int N, int Hp, int Wp)
 {
     constexpr int PPT = TH * TW / 32;
+    constexpr int NV = STAT ? 10 : 9;                       // values reduced per (tile, splat)
     __shared__ __align__(128) SplatRec s_rec[WARPS_PER_BLOCK][2][32];
     __shared__ __align__(8) uint64_t s_bar[WARPS_PER_BLOCK][2];
+    __shared__ __align__(16) float s_acc[DEFER ? WARPS_PER_BLOCK : 1][DEFER ? LGS_RG * NV : 1][LGS_ROWF];
     const int lane = threadIdx.x, warp = threadIdx.y, b = blockIdx.y;
     const int slot = blockIdx.x * blockDim.y + warp;
     int tile_id;
@@ -385,6 +395,23 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_kernel(
     kmax = __reduce_max_sync(FULL_MASK, kmax);
     if (kmax <= 0) return;
 
+    int pend = 0, pid0 = 0, pid1 = 0, pid2 = 0;        // DEFER: splats parked in s_acc and their ids (warp-uniform)
+    auto flush = [&]() {
+        __syncwarp();
+        if (lane < pend * NV) {
+            const float4* r4 = reinterpret_cast<const float4*>(&s_acc[DEFER ? warp : 0][DEFER ? lane : 0][0]);
+            float4 x0 = r4[0], x1 = r4[1], x2 = r4[2], x3 = r4[3], x4 = r4[4], x5 = r4[5], x6 = r4[6], x7 = r4[7];
+            float sum = (((x0.x + x0.y) + (x0.z + x0.w)) + ((x1.x + x1.y) + (x1.z + x1.w))) +
+                        (((x2.x + x2.y) + (x2.z + x2.w)) + ((x3.x + x3.y) + (x3.z + x3.w))) +
+                        ((((x4.x + x4.y) + (x4.z + x4.w)) + ((x5.x + x5.y) + (x5.z + x5.w))) +
+                         (((x6.x + x6.y) + (x6.z + x6.w)) + ((x7.x + x7.y) + (x7.z + x7.w))));
+            const int sp = lane / NV, v = lane - sp * NV;
+            const int pid = sp == 0 ? pid0 : (sp == 1 ? pid1 : pid2);
+            atomicAdd(&grad[(size_t)pid * LGS_GRAD_FLOATS + v], sum);                            // RED.ADD.F32
+        }
+        __syncwarp();
+        pend = 0;
+    };
     Stager<BULK> st;
     st.init(&s_rec[warp][0][0], &s_bar[warp][0], lane);
     const int nchunks = (kmax + 31) >> 5;
@@ -448,23 +475,35 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_kernel(
                 v8[3] = -dx * s1;                          // d B (total)
                 v8[4] = -0.5f * s2;                        // d C
                 v8[5] = dr; v8[6] = dg; v8[7] = db;
-                const float tot = butterfly8(v8, lane);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) dop += __shfl_xor_sync(FULL_MASK, dop, o);
-                if (STAT) {
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) esq += __shfl_xor_sync(FULL_MASK, esq, o);
-                }
                 const int pid = __shfl_sync(FULL_MASK, id_this, kk);
-                int slotv = -1; float val = 0.f;
-                if ((lane & 3) == 0) { slotv = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); val = tot; }
-                else if (lane == 1) { slotv = 8; val = dop; }
-                else if (STAT && lane == 2) { slotv = 9; val = esq; }
-                if (slotv >= 0) atomicAdd(&grad[(size_t)pid * LGS_GRAD_FLOATS + slotv], val);   // RED.ADD.F32, result unused
+                if (DEFER) {
+                    float* row = &s_acc[DEFER ? warp : 0][DEFER ? pend * NV : 0][lane];
+#pragma unroll
+                    for (int v = 0; v < 8; v++) row[v * LGS_ROWF] = v8[v];
+                    row[8 * LGS_ROWF] = dop;
+                    if (STAT) row[9 * LGS_ROWF] = esq;
+                    if (pend == 0) pid0 = pid; else if (pend == 1) pid1 = pid; else pid2 = pid;
+                    pend++;
+                    if (pend == LGS_RG) flush();
+                } else {
+                    const float tot = butterfly8(v8, lane);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) dop += __shfl_xor_sync(FULL_MASK, dop, o);
+                    if (STAT) {
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) esq += __shfl_xor_sync(FULL_MASK, esq, o);
+                    }
+                    int slotv = -1; float val = 0.f;
+                    if ((lane & 3) == 0) { slotv = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); val = tot; }
+                    else if (lane == 1) { slotv = 8; val = dop; }
+                    else if (STAT && lane == 2) { slotv = 9; val = esq; }
+                    if (slotv >= 0) atomicAdd(&grad[(size_t)pid * LGS_GRAD_FLOATS + slotv], val);   // RED.ADD.F32, result unused
+                }
             }
         }
         __syncwarp();
     }
+    if (DEFER && pend > 0) flush();
     st.drain();
 }
 
@@ -503,6 +542,18 @@ static bool use_bulk()
     return g_use_bulk == 1;
 }
 extern "C" int lgs_set_staging(int bulk) { g_use_bulk = bulk ? 1 : 0; return LGS_OK; }
+
+// backward reduction flavour: 1 = shared-memory deferred (default), 0 = register butterfly.  env LGS_BWD_REDUCE=butterfly|smem
+static int g_defer = -1;
+static bool use_deferred_reduce()
+{
+    if (g_defer < 0) {
+        const char* e = getenv("LGS_BWD_REDUCE");
+        g_defer = (e && e[0] == 'b') ? 0 : 1;
+    }
+    return g_defer == 1;
+}
+extern "C" int lgs_set_backward_reduce(int deferred) { g_defer = deferred ? 1 : 0; return LGS_OK; }
 
 // warps (= tiles) per CTA for the raster kernels: 1, 2 or 4.  Warps of a CTA are independent (no block-level
 // synchronisation), so this only trades CTA-retirement granularity against launch overhead.
@@ -586,7 +637,9 @@ extern "C" int lgs_rasterize_backward(const int* sorted_points, const int* start
         const SplatRec* recs = (const SplatRec*)packed_params;
         const bool bulk = use_bulk();
         const bool trans = d_trans_img != nullptr;
-#define BWD(S, T, B) raster_backward_kernel<TH, TW, S, T, B><<<grid, block, 0, st>>>(sorted_points, start_index, recs, specific_tiles, \
+        const bool defer = use_deferred_reduce() && !bulk;
+#define BWD(S, T, B) if (defer) BWD2(S, T, false, true); else BWD2(S, T, B, false)
+#define BWD2(S, T, B, D) raster_backward_kernel<TH, TW, S, T, B, D><<<grid, block, 0, st>>>(sorted_points, start_index, recs, specific_tiles, \
         n_specific, final_transmittance, last_contributor, d_img, d_trans_img, clamped_img, packed_grad, gx, ntile, cap, N, Hp, Wp)
         LGS_DISPATCH_TILE(tile_h, tile_w,
             if (enable_statistic) { if (trans) { if (bulk) BWD(true, true, true); else BWD(true, true, false); }
@@ -594,6 +647,7 @@ extern "C" int lgs_rasterize_backward(const int* sorted_points, const int* start
             else { if (trans) { if (bulk) BWD(false, true, true); else BWD(false, true, false); }
                    else { if (bulk) BWD(false, false, true); else BWD(false, false, false); } })
 #undef BWD
+#undef BWD2
         LGS_CHECK_LAUNCH("raster_backward_kernel");
     }
     if (d_ndc != nullptr) {
