@@ -254,11 +254,9 @@ __global__ void project_backward_kernel(
     const bool any = (ga.x != 0.f) | (ga.y != 0.f) | (ga.z != 0.f) | (ga.w != 0.f) | (gb.x != 0.f) | (gb.y != 0.f) |
                      (gb.z != 0.f) | (gb.w != 0.f) | (gc.x != 0.f);
     float o_pos[3] = { 0.f, 0.f, 0.f }, o_sc[3] = { 0.f, 0.f, 0.f }, o_q[4] = { 0.f, 0.f, 0.f, 0.f }, o_op = 0.f;
-    float o_sh[3][K];
+    float shb[16], dcol3[3] = { 0.f, 0.f, 0.f };       // SH basis and colour gradient: d sh[k][c] = shb[k] * dcol3[c]
 #pragma unroll
-    for (int c = 0; c < 3; c++)
-#pragma unroll
-        for (int k = 0; k < K; k++) o_sh[c][k] = 0.f;
+    for (int k = 0; k < 16; k++) shb[k] = 0.f;
     if (any) {
         float p[3] = { pos[src], pos[CS + src], pos[2 * CS + src] };
         float sr_[3] = { scale[src], scale[CS + src], scale[2 * CS + src] };
@@ -317,30 +315,40 @@ __global__ void project_backward_kernel(
 #pragma unroll
         for (int k = 0; k < 3; k++) o_pos[k] = dv[0] * Vm[k * 4] + dv[1] * Vm[k * 4 + 1] + dv[2] * Vm[k * 4 + 2] + dv[3] * Vm[k * 4 + 3];
         // SH coefficients (GR/compact.cu:655-823); the direction is treated as constant
-        float b[16];
-        lgs_sh_basis<DEG>(t.dirn[0], t.dirn[1], t.dirn[2], b);
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-#pragma unroll
-            for (int k = 0; k < K; k++) o_sh[c][k] = b[k] * dcol[c];
+        lgs_sh_basis<DEG>(t.dirn[0], t.dirn[1], t.dirn[2], shb);
+        dcol3[0] = dcol[0]; dcol3[1] = dcol[1]; dcol3[2] = dcol[2];
     }
     if (accumulate) {
         // dense accumulation: outputs are the full [..,C,S] gradient tensors, this view's contribution is added at
         // the SOURCE chunk (each Gaussian is owned by exactly one thread of one launch: no atomics needed);
         // Gaussians that received no gradient are not touched at all.
+        // The read-modify-writes are issued in batches (all loads of a batch first, then the stores) so that 11-16
+        // independent L2 round trips are in flight per thread instead of one dependent load->add->store chain each.
         if (any) {
+            float old[11];
 #pragma unroll
-            for (int k = 0; k < 3; k++) g_pos[k * CS + src] += o_pos[k];
+            for (int k = 0; k < 3; k++) old[k] = g_pos[k * CS + src];
 #pragma unroll
-            for (int k = 0; k < 3; k++) g_scale[k * CS + src] += o_sc[k];
+            for (int k = 0; k < 3; k++) old[3 + k] = g_scale[k * CS + src];
 #pragma unroll
-            for (int k = 0; k < 4; k++) g_rot[k * CS + src] += o_q[k];
-            g_opac[src] += o_op;
+            for (int k = 0; k < 4; k++) old[6 + k] = g_rot[k * CS + src];
+            old[10] = g_opac[src];
+#pragma unroll
+            for (int k = 0; k < 3; k++) g_pos[k * CS + src] = old[k] + o_pos[k];
+#pragma unroll
+            for (int k = 0; k < 3; k++) g_scale[k * CS + src] = old[3 + k] + o_sc[k];
+#pragma unroll
+            for (int k = 0; k < 4; k++) g_rot[k * CS + src] = old[6 + k] + o_q[k];
+            g_opac[src] = old[10] + o_op;
 #pragma unroll
             for (int c = 0; c < 3; c++) {
-                g_sh0[c * CS + src] += o_sh[c][0];
+                float osh[K];
+                osh[0] = g_sh0[c * CS + src];
 #pragma unroll
-                for (int k = 1; k < K; k++) g_shr[((size_t)(k - 1) * 3 + c) * CS + src] += o_sh[c][k];
+                for (int k = 1; k < K; k++) osh[k] = g_shr[((size_t)(k - 1) * 3 + c) * CS + src];
+                g_sh0[c * CS + src] = fmaf(shb[0], dcol3[c], osh[0]);
+#pragma unroll
+                for (int k = 1; k < K; k++) g_shr[((size_t)(k - 1) * 3 + c) * CS + src] = fmaf(shb[k], dcol3[c], osh[k]);
             }
         }
         return;
@@ -354,9 +362,9 @@ __global__ void project_backward_kernel(
     g_opac[dst] = o_op;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        g_sh0[c * AS + dst] = o_sh[c][0];
+        g_sh0[c * AS + dst] = shb[0] * dcol3[c];
 #pragma unroll
-        for (int k = 1; k < K; k++) g_shr[((size_t)(k - 1) * 3 + c) * AS + dst] = o_sh[c][k];
+        for (int k = 1; k < K; k++) g_shr[((size_t)(k - 1) * 3 + c) * AS + dst] = shb[k] * dcol3[c];
     }
     (void)rest_dim;
 }
