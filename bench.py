@@ -119,6 +119,7 @@ class StageTimer:
     def __init__(self):
         self.enabled = False
         self.rec = {}
+        self.sort_kernels = 0          # kernels launched by our own radix sort (3 per pass: histogram, row scan, scatter)
 
     def install(self):
         import torch
@@ -134,6 +135,11 @@ class StageTimer:
             orig(name, *a)
             e1.record()
             timer.rec.setdefault(name, []).append((e0, e1))
+            if os.environ.get("LGS_SORT", "lgs") != "cub":
+                if name in ("lgs_sort_pairs_u16", "lgs_sort_pairs_u32"):
+                    timer.sort_kernels += 3 * ((int(a[6]) - int(a[5]) + 7) // 8)
+                elif name == "lgs_sort_pairs_u32_rebased":
+                    timer.sort_kernels += 3 * ((int(a[6]) + 7) // 8)
         _lib.call = call
 
     def summary(self):
@@ -457,21 +463,12 @@ def run_ours(args, rank, world, local_rank):
     n_views_rank = vpr * args.steps
     bytes_per = stage_bytes(stats, S, K)
     stages = {}
-    sort_calls = summ.get("lgs_sort_pairs_u32")
     for name, (tot, n) in summ.items():
         stages[name] = {"ms_per_view": tot / n_views_rank, "launches_per_view": n / n_views_rank}
-    # the depth sort and (with 32-bit tile keys) the tile sort share an entry point: split by call parity
-    if "lgs_sort_pairs_u32" in timer.rec:
-        evs = timer.rec["lgs_sort_pairs_u32"]
-        if "lgs_sort_pairs_u16" in timer.rec:            # 16-bit tile keys: every u32 sort is the depth sort
-            stages["lgs_sort_pairs_u32(depth)"] = stages.pop("lgs_sort_pairs_u32")
-            stages["lgs_sort_pairs_u16(tile)"] = stages.pop("lgs_sort_pairs_u16")
-        else:
-            d = sum(a.elapsed_time(b) for a, b in evs[0::2]) / n_views_rank
-            tl = sum(a.elapsed_time(b) for a, b in evs[1::2]) / n_views_rank
-            stages["lgs_sort_pairs_u32(depth)"] = {"ms_per_view": d, "launches_per_view": 1.0}
-            stages["lgs_sort_pairs_u32(tile)"] = {"ms_per_view": tl, "launches_per_view": 1.0}
-            del stages["lgs_sort_pairs_u32"]
+    for old, new in (("lgs_sort_pairs_u32_rebased", "lgs_sort_pairs_u32(depth)"), ("lgs_sort_pairs_u32", "lgs_sort_pairs_u32(tile)"),
+                     ("lgs_sort_pairs_u16", "lgs_sort_pairs_u16(tile)")):
+        if old in stages:
+            stages[new] = stages.pop(old)
     for name, s_ in stages.items():
         b = bytes_per.get(name)
         if b is not None and s_["ms_per_view"] > 0:
@@ -508,6 +505,7 @@ def run_ours(args, rank, world, local_rank):
         if name in hand_written:
             mult = {"lgs_tile_range": 2, "lgs_tile_range_u16": 2}.get(name, 1)       # fill + range kernels
             gpu_launches += n * mult
+    gpu_launches += timer.sort_kernels
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

@@ -136,13 +136,20 @@ int lgs_tile_range(const int* table_tile_id, int V, int table_length, int max_ti
 int lgs_tile_range_u16(const unsigned short* table_tile_id, int V, int table_length, int max_tile_id, int fix_last,
                        int* tile_range, void* stream);
 
-/* building blocks of the fused pipeline (cub radix sort / scan on the caller's stream and workspace) */
+/* building blocks of the fused pipeline, on the caller's stream and workspace.  Stable LSD radix sort of (key, value)
+ * pairs on the bits [begin_bit, end_bit): replaces torch.sort (wrapper.py:739) for the depth order and
+ * cub::DeviceRadixSort::SortPairs (GR/binning.cu:204-221) for the tile sort.  keys_in/vals_in are not modified.
+ * lgs_set_sort_impl: 1 = own histogram/scan/scatter passes (default), 0 = cub::DeviceRadixSort; env LGS_SORT=lgs|cub. */
+int lgs_set_sort_impl(int impl);
 int lgs_sort_pairs_u16_workspace_bytes(int n, size_t* bytes);
 int lgs_sort_pairs_u16(const unsigned short* keys_in, unsigned short* keys_out, const unsigned* vals_in, unsigned* vals_out,
                        int n, int begin_bit, int end_bit, void* workspace, size_t workspace_bytes, void* stream);
 int lgs_sort_pairs_u32_workspace_bytes(int n, size_t* bytes);
 int lgs_sort_pairs_u32(const unsigned* keys_in, unsigned* keys_out, const unsigned* vals_in, unsigned* vals_out, int n,
                        int begin_bit, int end_bit, void* workspace, size_t workspace_bytes, void* stream);
+/* order by (key - bias) on bits [0, end_bit): the full-key order for keys inside [bias, bias + 2^end_bit), fewer passes */
+int lgs_sort_pairs_u32_rebased(const unsigned* keys_in, unsigned* keys_out, const unsigned* vals_in, unsigned* vals_out, int n,
+                               unsigned bias, int end_bit, void* workspace, size_t workspace_bytes, void* stream);
 int lgs_scan_gathered_workspace_bytes(int n, size_t* bytes);
 int lgs_scan_gathered(const int* counts, const unsigned* order, int n, int* out, void* workspace,
                       size_t workspace_bytes, void* stream);
@@ -193,7 +200,9 @@ int lgs_set_warps_per_block(int wpb);
  * A = number of allocated chunks (launch width; chunks >= *visible_chunks_num produce invisible records).
  * Outputs over A*S compacted slots: packed_params f32[A*S,12] (slots 10,11 carry ndc.x, ndc.y for the emit pass),
  * depth_key u32 (float bits of view z, 0xFFFFFFFF when invisible), iota u32 (slot index), tile_count i32,
- * totals i32[1] = number of (tile,splat) pairs. */
+ * totals i32[3] = { number of (tile,splat) pairs, ~min and max of the depth keys of the splats that have pairs }
+ * (so the depth sort can be limited to the bits in which those keys differ; splats without pairs may land anywhere
+ * in the order, they emit nothing). */
 int lgs_project_forward(int sh_degree, const int64_t* visible_chunk_id, const int* visible_chunks_num,
                         const float* view_matrix, const float* proj_matrix, const float* position, const float* scale,
                         const float* rotation, const float* sh_base, const float* sh_rest, const float* opacity, int C,

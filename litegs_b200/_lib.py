@@ -40,6 +40,7 @@ SIGNATURES = {
     "lgs_emit_pairs_u16": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "lgs_sort_pairs_u32_workspace_bytes": [_I, ctypes.POINTER(_Z)],
     "lgs_sort_pairs_u32": [_P, _P, _P, _P, _I, _I, _I, _P, _Z, _P],
+    "lgs_sort_pairs_u32_rebased": [_P, _P, _P, _P, _I, ctypes.c_uint, _I, _P, _Z, _P],
     "lgs_scan_gathered_workspace_bytes": [_I, ctypes.POINTER(_Z)],
     "lgs_scan_gathered": [_P, _P, _I, _P, _P, _Z, _P],
     "lgs_pack_params": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
@@ -47,6 +48,7 @@ SIGNATURES = {
     "lgs_rasterize_backward": [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I,
                                _P, _P, _P, _P, _P, _P, _P, _P],
     "lgs_set_staging": [_I],
+    "lgs_set_sort_impl": [_I],
     "lgs_set_warps_per_block": [_I],
     "lgs_set_backward_reduce": [_I],
     "lgs_project_forward": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],

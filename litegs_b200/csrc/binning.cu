@@ -5,7 +5,7 @@
 // depth-sorted once (N keys), pairs are emitted in that order at scanned offsets, then ONE stable LSD
 // radix sort over only the ceil(log2(tiles))+1 tile bits (2 passes at 1080p) groups them by tile while
 // preserving depth order.  cub::DeviceRadixSort (CCCL, header-only) provides the onesweep passes.
-#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_radix_sort.cuh>   // lgs_create_table (reference-compatible Level A path)
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
@@ -221,58 +221,8 @@ extern "C" int lgs_tile_range_u16(const unsigned short* table_tile_id, int V, in
 }
 
 // ------------------------------------------------------------------------------------------------
-// building blocks for the fused pipeline: u32 radix sort and "gather + inclusive scan".
+// building block for the fused pipeline: "gather + inclusive scan"   (the radix sorts live in sort.cu)
 // ------------------------------------------------------------------------------------------------
-extern "C" int lgs_sort_pairs_u32_workspace_bytes(int n, size_t* bytes)
-{
-    size_t tmp = 0;
-    cub::DeviceRadixSort::SortPairs<unsigned, unsigned>(nullptr, tmp, nullptr, nullptr, nullptr, nullptr, n, 0, 32);
-    *bytes = tmp + 256;
-    return LGS_OK;
-}
-
-extern "C" int lgs_sort_pairs_u32(const unsigned* keys_in, unsigned* keys_out, const unsigned* vals_in, unsigned* vals_out, int n,
-                                  int begin_bit, int end_bit, void* workspace, size_t workspace_bytes, void* stream)
-{
-    if (n <= 0) return LGS_OK;
-    size_t need = 0;
-    cub::DeviceRadixSort::SortPairs<unsigned, unsigned>(nullptr, need, nullptr, nullptr, nullptr, nullptr, n, begin_bit, end_bit);
-    void* ws = (void*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    if (workspace == nullptr || workspace_bytes < need + 256) {
-        lgs_set_error("sort_pairs_u32: workspace of %zu bytes needed, %zu given", need + 256, workspace_bytes);
-        return LGS_ERR_WORKSPACE;
-    }
-    LGS_CUDA(cub::DeviceRadixSort::SortPairs<unsigned, unsigned>(ws, need, keys_in, keys_out, vals_in, vals_out, n, begin_bit, end_bit,
-                                                                 (cudaStream_t)stream));
-    return LGS_OK;
-}
-
-// 16-bit tile keys (tiles+1 < 65536, i.e. anything up to 4K at 8x16): 6 instead of 8 bytes per pair and pass
-extern "C" int lgs_sort_pairs_u16_workspace_bytes(int n, size_t* bytes)
-{
-    size_t tmp = 0;
-    cub::DeviceRadixSort::SortPairs<unsigned short, unsigned>(nullptr, tmp, nullptr, nullptr, nullptr, nullptr, n, 0, 16);
-    *bytes = tmp + 256;
-    return LGS_OK;
-}
-
-extern "C" int lgs_sort_pairs_u16(const unsigned short* keys_in, unsigned short* keys_out, const unsigned* vals_in, unsigned* vals_out,
-                                  int n, int begin_bit, int end_bit, void* workspace, size_t workspace_bytes, void* stream)
-{
-    if (n <= 0) return LGS_OK;
-    LGS_REQUIRE(end_bit <= 16, "sort_pairs_u16: end_bit %d > 16", end_bit);
-    size_t need = 0;
-    cub::DeviceRadixSort::SortPairs<unsigned short, unsigned>(nullptr, need, nullptr, nullptr, nullptr, nullptr, n, begin_bit, end_bit);
-    void* ws = (void*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    if (workspace == nullptr || workspace_bytes < need + 256) {
-        lgs_set_error("sort_pairs_u16: workspace of %zu bytes needed, %zu given", need + 256, workspace_bytes);
-        return LGS_ERR_WORKSPACE;
-    }
-    LGS_CUDA(cub::DeviceRadixSort::SortPairs<unsigned short, unsigned>(ws, need, keys_in, keys_out, vals_in, vals_out, n, begin_bit, end_bit,
-                                                                       (cudaStream_t)stream));
-    return LGS_OK;
-}
-
 struct GatherCount {
     const int* counts; const unsigned* order;
     __host__ __device__ int operator()(int j) const { return counts[order[j]]; }

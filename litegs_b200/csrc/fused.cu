@@ -152,8 +152,29 @@ __global__ void project_forward_kernel(
     iota[dst] = (unsigned)dst;
     tile_count[dst] = count;
     // total number of (tile, splat) pairs: integer sum, order independent -> deterministic
+    // totals: pair count (integer sum: order independent, deterministic) and the range of the depth keys that matter
+    // (splats with pairs) so that the host can sort only the bits of that range.  totals[1] holds max(~key) so that a
+    // zero fill initialises both.  One set of atomics per block.
+    __shared__ int s_sum[32];
+    __shared__ unsigned s_min[32], s_max[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     int wsum = __reduce_add_sync(0xffffffffu, count);
-    if ((threadIdx.x & 31) == 0 && wsum != 0) atomicAdd(&totals[0], wsum);
+    unsigned wmin = __reduce_min_sync(0xffffffffu, count > 0 ? key : 0xFFFFFFFFu);
+    unsigned wmax = __reduce_max_sync(0xffffffffu, count > 0 ? key : 0u);
+    if (lane == 0) { s_sum[wid] = wsum; s_min[wid] = wmin; s_max[wid] = wmax; }
+    __syncthreads();
+    if (wid == 0) {
+        int bs = lane < nw ? s_sum[lane] : 0;
+        unsigned bmin = lane < nw ? s_min[lane] : 0xFFFFFFFFu, bmax = lane < nw ? s_max[lane] : 0u;
+        bs = __reduce_add_sync(0xffffffffu, bs);
+        bmin = __reduce_min_sync(0xffffffffu, bmin);
+        bmax = __reduce_max_sync(0xffffffffu, bmax);
+        if (lane == 0 && bs != 0) {
+            atomicAdd(&totals[0], bs);
+            atomicMax((unsigned*)&totals[1], ~bmin);
+            atomicMax((unsigned*)&totals[2], bmax);
+        }
+    }
 }
 
 extern "C" int lgs_project_forward(int sh_degree, const int64_t* visible_chunk_id, const int* visible_chunks_num,
@@ -167,7 +188,7 @@ extern "C" int lgs_project_forward(int sh_degree, const int64_t* visible_chunk_i
     LGS_REQUIRE(lgs_tile_ok(tile_h, tile_w), "project_forward: tile %dx%d not one of 8x16, 12x16, 16x16, 8x8", tile_h, tile_w);
     LGS_REQUIRE(S >= 32 && S <= 1024 && S % 32 == 0, "project_forward: chunk size %d must be a multiple of 32 in 32..1024", S);
     cudaStream_t st = (cudaStream_t)stream;
-    LGS_CUDA(cudaMemsetAsync(totals, 0, sizeof(int), st));
+    LGS_CUDA(cudaMemsetAsync(totals, 0, 3 * sizeof(int), st));
     if (A == 0) return LGS_OK;
     int gx = (img_w + tile_w - 1) / tile_w, gy = (img_h + tile_h - 1) / tile_h;
 #define PF(D) project_forward_kernel<D, TH, TW><<<A, S, 0, st>>>(visible_chunk_id, visible_chunks_num, view_matrix, proj_matrix, position, \
@@ -180,21 +201,51 @@ extern "C" int lgs_project_forward(int sh_degree, const int64_t* visible_chunk_i
 }
 
 // (tile+1, splat) emission in depth order from the packed record.    replaces GR/binning.cu:33-110
+// One splat per lane.  A warp's 32 splats own one contiguous run [wbase, wend) of the pair list (the offsets
+// are a scan in the same order), so the lanes stage their pairs in a per-warp shared-memory window and the
+// warp then copies the window out with fully coalesced stores; without the staging every lane streams its own
+// run and the kernel sits on the LSU queue (ncu: lg_throttle was the top stall).  Runs longer than the window
+// are handled by walking again per window (rare: near-camera splats).
+constexpr int LGS_EMIT_WARPS = 8;
+#ifndef LGS_EMIT_WINDOW
+#define LGS_EMIT_WINDOW 512
+#endif
 template <int TH, int TW, typename KeyT>
-__global__ void __launch_bounds__(256) emit_pairs_rec_kernel(const SplatRec* __restrict__ recs, const int* __restrict__ offset,
+__global__ void __launch_bounds__(LGS_EMIT_WARPS * 32) emit_pairs_rec_kernel(const SplatRec* __restrict__ recs, const int* __restrict__ offset,
                                                              const unsigned* __restrict__ order, int n, int cap, int H, int W,
                                                              int gx, int gy, KeyT* __restrict__ keys, int* __restrict__ vals)
 {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    int off = j == 0 ? 0 : offset[j - 1];
-    int asz = offset[j] - off;
-    if (asz <= 0 || off + asz > cap) return;
-    int i = (int)order[j];
-    const SplatRec r = recs[i];
+    __shared__ KeyT s_keys[LGS_EMIT_WARPS][LGS_EMIT_WINDOW];
+    __shared__ int s_vals[LGS_EMIT_WARPS][LGS_EMIT_WINDOW];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j - lane >= n) return;                               // whole warp past the end
+    int off = 0, asz = 0, i = 0;
+    if (j < n) {
+        off = j == 0 ? 0 : offset[j - 1];
+        asz = offset[j] - off;
+        if (asz <= 0 || off + asz > cap) asz = 0;
+        i = (int)order[j];
+    }
     SplatGeom g;
-    lgs_splat_setup<TH, TW>(r.pad0, r.pad1, 1.0f, r.A, r.B, r.C, r.o, H, W, gx, gy, false, g);
-    if (g.visible) lgs_process_tiles<TH, TW, true, KeyT>(g, gx, i, off, cap, keys, vals);
+    g.visible = false;
+    if (asz > 0) {
+        const SplatRec r = recs[i];
+        lgs_splat_setup<TH, TW>(r.pad0, r.pad1, 1.0f, r.A, r.B, r.C, r.o, H, W, gx, gy, false, g);
+    }
+    const bool live = asz > 0 && g.visible;
+    const int wbase = __reduce_min_sync(0xffffffffu, live ? off : 0x7fffffff);
+    const int wend = __reduce_max_sync(0xffffffffu, live ? off + asz : 0);
+    KeyT* sk = s_keys[wid];
+    int* sv = s_vals[wid];
+    for (int lo = wbase; lo < wend; lo += LGS_EMIT_WINDOW) {
+        if (live && off < lo + LGS_EMIT_WINDOW && off + asz > lo)
+            lgs_process_tiles<TH, TW, true, KeyT>(g, gx, i, off, LGS_EMIT_WINDOW, sk, sv, lo);
+        __syncwarp();
+        const int m = min(LGS_EMIT_WINDOW, wend - lo);
+        for (int k = lane; k < m; k += 32) { keys[lo + k] = sk[k]; vals[lo + k] = sv[k]; }
+        __syncwarp();
+    }
 }
 
 extern "C" int lgs_emit_pairs(const float* packed_params, const int* offset, const unsigned* order, int n, int cap, int img_h,
@@ -205,7 +256,7 @@ extern "C" int lgs_emit_pairs(const float* packed_params, const int* offset, con
     int gx = (img_w + tile_w - 1) / tile_w, gy = (img_h + tile_h - 1) / tile_h;
     cudaStream_t st = (cudaStream_t)stream;
     LGS_DISPATCH_TILE(tile_h, tile_w,
-        emit_pairs_rec_kernel<TH, TW, int><<<lgs_cdiv(n, 256), 256, 0, st>>>((const SplatRec*)packed_params, offset, order, n, cap, img_h,
+        emit_pairs_rec_kernel<TH, TW, int><<<lgs_cdiv(n, LGS_EMIT_WARPS * 32), LGS_EMIT_WARPS * 32, 0, st>>>((const SplatRec*)packed_params, offset, order, n, cap, img_h,
                                                                            img_w, gx, gy, keys, vals);)
     LGS_CHECK_LAUNCH("emit_pairs_rec_kernel");
     return LGS_OK;
@@ -221,7 +272,7 @@ extern "C" int lgs_emit_pairs_u16(const float* packed_params, const int* offset,
     LGS_REQUIRE(gx * gy + 1 < 65536, "emit_pairs_u16: %d tiles do not fit 16-bit keys", gx * gy);
     cudaStream_t st = (cudaStream_t)stream;
     LGS_DISPATCH_TILE(tile_h, tile_w,
-        emit_pairs_rec_kernel<TH, TW, unsigned short><<<lgs_cdiv(n, 256), 256, 0, st>>>((const SplatRec*)packed_params, offset, order, n, cap,
+        emit_pairs_rec_kernel<TH, TW, unsigned short><<<lgs_cdiv(n, LGS_EMIT_WARPS * 32), LGS_EMIT_WARPS * 32, 0, st>>>((const SplatRec*)packed_params, offset, order, n, cap,
                                                                                       img_h, img_w, gx, gy, keys, vals);)
     LGS_CHECK_LAUNCH("emit_pairs_rec_kernel<u16>");
     return LGS_OK;

@@ -69,10 +69,11 @@ __device__ __forceinline__ void lgs_splat_setup(float ndcx, float ndcy, float vi
 }
 
 // Walks the tile slices of one splat; returns the number of tiles and, when EMIT, writes
-// (tile id + 1, idx) pairs to keys/vals[off ...) guarded by cap.
+// (tile id + 1, idx) pairs number off, off+1, ... to keys/vals[k - lo] for those k inside the window
+// [lo, lo + cap)  (lo = 0: plain bounds guard; lo > 0: staging a window of the list in shared memory).
 template <int TH, int TW, bool EMIT, typename KeyT = int>
 __device__ __forceinline__ int lgs_process_tiles(const SplatGeom& g, int gx, int idx, int off, int cap,
-                                                 KeyT* __restrict__ keys, int* __restrict__ vals)
+                                                 KeyT* __restrict__ keys, int* __restrict__ vals, int lo = 0)
 {
     int y_span = g.rect_max[1] - g.rect_min[1], x_span = g.rect_max[0] - g.rect_min[0];
     if (y_span * x_span <= 0) return 0;
@@ -102,7 +103,8 @@ __device__ __forceinline__ int lgs_process_tiles(const SplatGeom& g, int gx, int
         if (EMIT) {
             for (int v = min_v; v < max_v; v++) {
                 int key = isY ? (u * gx + v) : (v * gx + u);
-                if (off < cap) { keys[off] = (KeyT)(key + 1); vals[off] = idx; }
+                unsigned rel = (unsigned)(off - lo);
+                if (rel < (unsigned)cap) { keys[rel] = (KeyT)(key + 1); vals[rel] = idx; }
                 off++;
             }
         }

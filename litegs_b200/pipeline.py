@@ -2,12 +2,12 @@
 
 One view = render_preprocess + render of the reference (litegs/render/__init__.py:11-94) collapsed to
 
-    cull_chunks -> project_forward -> [one 8-byte D2H of the two sizes] -> depth radix sort (N keys) ->
+    cull_chunks -> project_forward -> [one 16-byte D2H: sizes + depth-key range] -> depth radix sort (N keys) ->
     gathered scan -> emit_pairs -> tile radix sort (tile bits only) -> tile_range -> raster_forward
 
 and the backward to  raster_backward -> project_backward  (two kernels + one memset).  Everything runs on
-the current CUDA stream; the only host synchronisation is the read-back of (visible chunks, pair count)
-that sizes the sort, exactly one per view (the reference pays two: GR/compact.cu:527-549 and
+the current CUDA stream; the only host synchronisation is the 16-byte read-back of (visible chunks, pair
+count, depth-key range) that sizes the sorts, exactly one per view (the reference pays two: GR/compact.cu:527-549 and
 GR/binning.cu:137-163, hidden behind last epoch's feedback values when available).
 """
 from __future__ import annotations
@@ -50,7 +50,7 @@ class ViewState:
     n_chunks_visible: int
     n_pairs: int
     chunk_ids: torch.Tensor          # i64[M], first n_chunks_visible valid, ascending
-    counters: torch.Tensor           # i32[2] = (visible chunks, pairs) on device
+    counters: torch.Tensor           # i32[4] = (visible chunks, pairs, ~min depth key, max depth key) on device
     view: torch.Tensor
     proj: torch.Tensor
     packed: torch.Tensor             # f32[1, Nv, 12]
@@ -62,14 +62,14 @@ class ViewState:
 
 
 class _Pinned:
-    """Per-device pinned int32[2] used for the size read-back."""
+    """Per-device pinned int32[4] used for the size read-back (visible chunks, pairs, ~min depth key, max depth key)."""
     _bufs: dict = {}
 
     @classmethod
     def get(cls, dev) -> torch.Tensor:
         b = cls._bufs.get(dev)
         if b is None:
-            b = cls._bufs[dev] = torch.zeros(2, dtype=_I32).pin_memory()
+            b = cls._bufs[dev] = torch.zeros(4, dtype=_I32).pin_memory()
         return b
 
 
@@ -96,7 +96,7 @@ def render_view_forward(params: dict, cluster_origin: torch.Tensor, cluster_exte
     M = C
     with torch.cuda.device(dev):
         st = _stream(dev)
-        counters = torch.empty(2, dtype=_I32, device=dev)
+        counters = torch.empty(4, dtype=_I32, device=dev)
         vis = torch.empty(M, dtype=_U8, device=dev)
         ids = torch.empty(M, dtype=_I64, device=dev)
         _lib.call("lgs_frustum_culling_aabb", _ptr(cluster_origin), _ptr(cluster_extend), _ptr(frustumplane), M, 1, _ptr(vis),
@@ -114,16 +114,21 @@ def render_view_forward(params: dict, cluster_origin: torch.Tensor, cluster_exte
         pinned.copy_(counters, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
         nvis, D = int(pinned[0]), int(pinned[1])
+        kmin, kmax = ~int(pinned[2]) & 0xFFFFFFFF, int(pinned[3]) & 0xFFFFFFFF
         Nv = nvis * S
 
         ranges = torch.empty((1, ntile + 2), dtype=_I32, device=dev)
         if D > 0:
-            # depth order of the Nv live slots (stable LSD radix sort on the float bits of view z)
+            # depth order of the Nv live slots: stable LSD radix sort on the float bits of view z, rebased to the
+            # smallest key of a splat that owns pairs and limited to the bits of the key range (z in [1.3, 4.7) spans 31
+            # bits of float pattern but 24 bits of range: 3 passes instead of 4); where a splat without pairs lands in
+            # the order is irrelevant, it emits nothing
+            depth_bits = max(1, (kmax - kmin).bit_length()) if kmax >= kmin else 1
             nb = _query_bytes("lgs_sort_pairs_u32_workspace_bytes", _round_up(Nv, 1 << 16))
             ws = torch.empty(nb, dtype=_U8, device=dev)
             dkey_s = torch.empty(Nv, dtype=_I32, device=dev)
             order = torch.empty(Nv, dtype=_I32, device=dev)
-            _lib.call("lgs_sort_pairs_u32", _ptr(dkey), _ptr(dkey_s), _ptr(iota), _ptr(order), Nv, 0, 32, _ptr(ws),
+            _lib.call("lgs_sort_pairs_u32_rebased", _ptr(dkey), _ptr(dkey_s), _ptr(iota), _ptr(order), Nv, kmin, depth_bits, _ptr(ws),
                       ctypes.c_size_t(nb), st)
             nb2 = _query_bytes("lgs_scan_gathered_workspace_bytes", _round_up(Nv, 1 << 16))
             ws2 = ws if nb2 <= nb else torch.empty(nb2, dtype=_U8, device=dev)
