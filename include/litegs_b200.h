@@ -239,9 +239,38 @@ int lgs_adam_update_primitive(float* param, const float* grad, float* exp_avg, f
                               const int64_t* primitive_visible, int R, int N, double lr, double b1, double b2,
                               double eps, void* stream);
 
+/* The optimizer step of the multi-view / data-parallel path: ONE launch for all six parameter tensors, from the dense
+ * gradient buffer grad f32[rows, C, S] (rows = sum rows_per_param, parameter k occupies its rows in the order xyz,
+ * scale, rot, sh_0, sh_rest, opacity) and moment buffers of the same shape.  Replaces the six adamUpdate calls of
+ * optimizer.py:14-44 with the same arithmetic (GR/compact.cu:320-344, no bias correction).  params, rows_per_param,
+ * lr_per_param are HOST arrays of 6.  touched f32[C] (may be NULL = all chunks): only chunks with touched != 0 update;
+ * lgs_mark_visible_chunks sets it from a view's visible-chunk list.  clear_grad: also zero the consumed gradient
+ * rows and marks (so the buffer needs no memset between steps). */
+int lgs_mark_visible_chunks(const int64_t* visible_chunk_id, const int* visible_chunks_num, int A, float* touched, void* stream);
+int lgs_adam_step_dense(float* const* params, const int* rows_per_param, const float* lr_per_param, float* grad,
+                        float* exp_avg, float* exp_avg_sq, float* touched, int C, int S, double b1, double b2, double eps,
+                        int clear_grad, void* stream);
+
 /* gpu_driven_pipeline_sparse_op, GR/compact.cu:1221-1336 (GR/compact.h:35-41). dtype 0=f32 1=i32; op 0=add 1=min 2=max */
 int lgs_sparse_chunk_op(void* A, const void* B, const int64_t* visible_chunk_ids, const int* visible_count, int dtype,
                         int op, int ele_num, int chunks, int alloc_chunks, int chunk_size, void* stream);
+
+/* ---- fused SSIM / L1 + SSIM loss (next row; what trainer.py:145 calls) ------------------ */
+
+/* fusedssim / fusedl1ssim_loss, fused_ssim/ssim.cu:444-479, 855-900 (kernels :64-274, :528-712).  img1, img2 f32[B,CH,H,W]
+ * on the device.  l1_mode 0: map = SSIM;  1: map = w (1 - SSIM) + (1 - w) |img1 - img2|.  11-tap sigma-1.5 Gaussian,
+ * zero padding ("same").  Outputs, each optional: map f32[B,CH,H,W]; the three partials dm_dmu1, dm_dsigma1_sq,
+ * dm_dsigma12 (all or none; NULL = the reference's train=false); block_sums f32[count of lgs_ssim_num_block_sums] = the sum
+ * of the map over each CTA's tile (the training path needs only the mean of the map: sum these in order). */
+int lgs_ssim_num_block_sums(int B, int CH, int H, int W, int* count);
+int lgs_ssim_forward(const float* img1, const float* img2, int B, int CH, int H, int W, float C1, float C2, int l1_mode,
+                     float ssim_weight, float* map, float* dm_dmu1, float* dm_dsigma1_sq, float* dm_dsigma12,
+                     float* block_sums, void* stream);
+/* fusedssim_backward / fusedl1ssim_loss_backward, fused_ssim/ssim.cu:487-524, 904-942 (kernels :277-437, :719-850):
+ * dL/dimg1 from dL/dmap and the saved partials.  dL_dmap NULL = the uniform value uniform_chain (loss = mean(map)). */
+int lgs_ssim_backward(const float* img1, const float* img2, const float* dL_dmap, float uniform_chain, const float* dm_dmu1,
+                      const float* dm_dsigma1_sq, const float* dm_dsigma12, int B, int CH, int H, int W, int l1_mode,
+                      float ssim_weight, float* dL_dimg1, void* stream);
 
 #ifdef __cplusplus
 }

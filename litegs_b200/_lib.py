@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblitegs_b200.so")
 
-_P, _I, _D, _Z = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_size_t
+_P, _I, _D, _Z, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_size_t, ctypes.c_float
 
 # name -> argument ctypes, in header order (include/litegs_b200.h)
 SIGNATURES = {
@@ -58,6 +58,11 @@ SIGNATURES = {
     "lgs_adam_update_chunk": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _D, _D, _D, _D, _P],
     "lgs_adam_update_primitive": [_P, _P, _P, _P, _P, _I, _I, _D, _D, _D, _D, _P],
     "lgs_sparse_chunk_op": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "lgs_mark_visible_chunks": [_P, _P, _I, _P, _P],
+    "lgs_adam_step_dense": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _D, _D, _D, _I, _P],
+    "lgs_ssim_num_block_sums": [_I, _I, _I, _I, ctypes.POINTER(_I)],
+    "lgs_ssim_forward": [_P, _P, _I, _I, _I, _I, _F, _F, _I, _F, _P, _P, _P, _P, _P, _P],
+    "lgs_ssim_backward": [_P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P],
 }
 NO_STATUS = {"lgs_last_error": ctypes.c_char_p, "lgs_abi_version": ctypes.c_int}
 

@@ -45,15 +45,32 @@ class GradAccumulator:
         C, S = self.shapes["xyz"][-2:]
         n_rows = self.rows["opacity"].stop
         dev = params["xyz"].device
-        self.buf = torch.zeros((n_rows, C, S), dtype=torch.float32, device=dev)
+        # one allocation = one all-reduce: [rows*C*S gradient | C chunk marks].  The marks say which chunks were visible
+        # in at least one view of the step (on any rank after the reduce); the fused optimizer step updates only those,
+        # the reference's sparse-Adam semantics (optimizer.py:14-44).
+        self.flat = torch.zeros(n_rows * C * S + C, dtype=torch.float32, device=dev)
+        self.buf = self.flat[: n_rows * C * S].view(n_rows, C, S)
+        self.touched = self.flat[n_rows * C * S:]
         self._work = None
         self._comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
 
     def zero_(self):
-        self.buf.zero_()
+        self.flat.zero_()
+
+    def mark(self, chunk_ids: torch.Tensor, visible_count: torch.Tensor):
+        """touched[chunk_ids[j]] = 1 for j < *visible_count (device count: no sync)."""
+        if self.touched.is_cuda:
+            from . import _lib
+            from .fused import _ptr, _stream
+            _lib.call("lgs_mark_visible_chunks", _ptr(chunk_ids), _ptr(visible_count), int(chunk_ids.shape[0]), _ptr(self.touched),
+                      _stream(self.touched.device))
+        else:
+            n = int(visible_count.reshape(-1)[0])
+            self.touched[chunk_ids[:n].long()] = 1.0
 
     def add_view(self, compacted: Dict[str, torch.Tensor], chunk_ids: torch.Tensor, visible_count: torch.Tensor):
         """buf[rows(k), chunk_ids[j], :] += compacted[k][..., j, :] for j < *visible_count (device count: no sync)."""
+        self.mark(chunk_ids, visible_count)
         for k in PARAM_ORDER:
             g = compacted[k]
             if g.numel() == 0:
@@ -81,9 +98,9 @@ class GradAccumulator:
         if self._comm_stream is not None and async_op:
             self._comm_stream.wait_stream(torch.cuda.current_stream(self.buf.device))
             with torch.cuda.stream(self._comm_stream):
-                self._work = dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, async_op=True)
+                self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=True)
         else:
-            dist.all_reduce(self.buf, op=dist.ReduceOp.SUM)
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
 
     def wait(self):
         if self._work is not None:
@@ -93,5 +110,8 @@ class GradAccumulator:
             torch.cuda.current_stream(self.buf.device).wait_stream(self._comm_stream)
 
     def grads(self) -> Dict[str, torch.Tensor]:
-        """Views of the buffer with the parameters' own shapes."""
-        return {k: self.buf[self.rows[k]].reshape(self.shapes[k]) for k in PARAM_ORDER}
+        """Views of the buffer with the parameters' own shapes, plus "_touched" (f32[C] chunk marks): the dict
+        render_view / render_views take as accumulate_into."""
+        out = {k: self.buf[self.rows[k]].reshape(self.shapes[k]) for k in PARAM_ORDER}
+        out["_touched"] = self.touched
+        return out

@@ -184,7 +184,7 @@ def render_view_backward(params: dict, state: ViewState, d_img: torch.Tensor, d_
 
     accumulate_into: dict of DENSE contiguous gradient tensors shaped like the parameters; when given, this
     view's gradients are added into them by the kernel itself and no compacted tensors are produced
-    (returns (None, packed_grad))."""
+    (returns (None, packed_grad)).  An optional "_touched" entry (f32[C]) receives 1 at every visible chunk."""
     xyz = params["xyz"]
     dev = xyz.device
     C, S = xyz.shape[-2:]
@@ -217,6 +217,9 @@ def render_view_backward(params: dict, state: ViewState, d_img: torch.Tensor, d_
                           _ptr(state.view), _ptr(state.proj), _ptr(xyz), _ptr(params["scale"]), _ptr(params["rot"]),
                           _ptr(params["opacity"]), C, S, A, R, H, W, int(CONFIG["true_sigmoid_grad"]), _ptr(pg), None, 2,
                           _ptr(d["xyz"]), _ptr(d["scale"]), _ptr(d["rot"]), _ptr(d["sh_0"]), _ptr(d["sh_rest"]), _ptr(d["opacity"]), st)
+                if d.get("_touched") is not None:       # chunk marks for the fused optimizer step (GradAccumulator.touched)
+                    _lib.call("lgs_mark_visible_chunks", _ptr(state.chunk_ids), ctypes.c_void_p(state.counters.data_ptr()), A,
+                              _ptr(d["_touched"]), st)
             return None, pg
         g_pos = torch.empty((3, A, S), dtype=_F32, device=dev)
         g_sc = torch.empty((3, A, S), dtype=_F32, device=dev)

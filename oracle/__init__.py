@@ -403,3 +403,48 @@ def render_forward_backward(params, chunk_aabb, camera, img_hw, tile_hw, sh_degr
                 grads=dict(zip(("xyz", "scale", "rot", "sh_0", "sh_rest", "opacity"), grads)),
                 inter=inter, ranges=ranges, sorted_pid=sorted_pid, color=color, opacity=opacity,
                 d_ndc=d_ndc, d_cov=d_cov, d_col=d_col, d_op=d_op)
+
+
+# ---------------------------------------------------------------------------------------------
+# fused_ssim-shaped entry points (fused_ssim/ext.cpp:4-9)
+# ---------------------------------------------------------------------------------------------
+
+def _ssim_forward(l1_mode, ssim_weight, C1, C2, img1, img2, train):
+    dt = img1.dtype
+    a, b = _c(img1), _c(img2, dt)
+    B, CH, H, W = a.shape
+    out = np.zeros_like(a)
+    d = [np.zeros_like(a) for _ in range(3)] if train else [None, None, None]
+    _call("orc_ssim_forward", dt, a, b, B, CH, H, W, float(C1), float(C2), int(l1_mode), float(ssim_weight), out, *d)
+    e = np.zeros((0,), dt)
+    return (out, d[0], d[1], d[2]) if train else (out, e, e, e)
+
+
+def _ssim_backward(l1_mode, ssim_weight, img1, img2, dL_dmap, dm_dmu1, dm_dsigma1_sq, dm_dsigma12):
+    dt = img1.dtype
+    a = _c(img1)
+    B, CH, H, W = a.shape
+    out = np.zeros_like(a)
+    _call("orc_ssim_backward", dt, a, _c(img2, dt), _c(dL_dmap, dt), _c(dm_dmu1, dt), _c(dm_dsigma1_sq, dt), _c(dm_dsigma12, dt),
+          B, CH, H, W, int(l1_mode), float(ssim_weight), out)
+    return out
+
+
+def fusedssim(C1, C2, img1, img2, train=True):
+    """ssim.cu:444-479 -> (ssim_map, dm_dmu1, dm_dsigma1_sq, dm_dsigma12)."""
+    return _ssim_forward(0, 0.0, C1, C2, img1, img2, train)
+
+
+def fusedssim_backward(C1, C2, img1, img2, dL_dmap, dm_dmu1, dm_dsigma1_sq, dm_dsigma12):
+    """ssim.cu:487-524 -> dL/dimg1."""
+    return _ssim_backward(0, 0.0, img1, img2, dL_dmap, dm_dmu1, dm_dsigma1_sq, dm_dsigma12)
+
+
+def fusedl1ssim_loss(ssim_weight, C1, C2, img1, img2, train=True):
+    """ssim.cu:855-900 -> (loss_map, dm_dmu1, dm_dsigma1_sq, dm_dsigma12)."""
+    return _ssim_forward(1, ssim_weight, C1, C2, img1, img2, train)
+
+
+def fusedl1ssim_loss_backward(ssim_weight, C1, C2, img1, img2, dL_dmap, dm_dmu1, dm_dsigma1_sq, dm_dsigma12):
+    """ssim.cu:904-942 -> dL/dimg1."""
+    return _ssim_backward(1, ssim_weight, img1, img2, dL_dmap, dm_dmu1, dm_dsigma1_sq, dm_dsigma12)

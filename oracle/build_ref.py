@@ -1,7 +1,7 @@
 """Recipe that compiles the UNMODIFIED reference extension (litegs/submodules/gaussian_raster) for sm_100a.
 
 TEST INFRASTRUCTURE ONLY.  Sources are compiled where they lie under /root/reference (nothing is
-copied into this repository); the only output is ``oracle/_ref/litegs_fused_ref.so`` (git-ignored,
+copied into this repository); the only outputs are ``oracle/_ref/litegs_fused_ref.so`` and ``oracle/_ref/fused_ssim_cuda_ref.so`` (git-ignored,
 NOT gpurun-ignored, so it travels to the GPU box).  It is the "reference itself run here" that pins the
 CPU oracle (tests/test_gpu_vs_reference.py, tests/golden/make_golden.py) and the CUDA baseline that
 ``bench.py`` times next to ours ("ref_cuda").  Flags are the reference's own: -O3 --use_fast_math
@@ -20,11 +20,16 @@ NAME = "litegs_fused_ref"
 SOURCES = ["binning.cu", "compact.cu", "cuda_errchk.cpp", "ext_cuda.cpp", "raster.cu", "transform.cu"]
 
 
-def so_path():
+REF_SSIM = "/root/reference/litegs/submodules/fused_ssim"
+SSIM_NAME = "fused_ssim_cuda_ref"
+SSIM_SOURCES = ["ssim.cu", "ext.cpp"]
+
+
+def so_path(name: str = NAME):
     if not os.path.isdir(OUT):
         return None
     for f in os.listdir(OUT):
-        if f.startswith(NAME) and f.endswith(".so"):
+        if f.startswith(name) and f.endswith(".so"):
             return os.path.join(OUT, f)
     return None
 
@@ -59,17 +64,59 @@ def build(quiet: bool = False):
     return so_path()
 
 
-def load():
-    """Import the prebuilt reference module (needs torch; used on the GPU box). Returns None if absent."""
-    p = so_path()
+def build_ssim(quiet: bool = False):
+    """Build oracle/_ref/fused_ssim_cuda_ref.so from the reference's fused_ssim/{ssim.cu,ext.cpp} with the reference's own
+    nvcc flags (fused_ssim/setup.py:33: --maxrregcount=32 --use_fast_math) plus the arch; returns the path or None."""
+    if so_path(SSIM_NAME) is not None:
+        return so_path(SSIM_NAME)
+    if not os.path.isdir(REF_SSIM):
+        if not quiet:
+            print("[build_ref] /root/reference not present: nothing to build")
+        return None
+    out = os.path.join(OUT, "ssim_build")
+    os.makedirs(out, exist_ok=True)
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
+    os.environ["CXX"] = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else os.environ.get("CXX", "g++")
+    os.environ["CC"] = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else os.environ.get("CC", "gcc")
+    from torch.utils import cpp_extension
+    cpp_extension.load(
+        name=SSIM_NAME,
+        sources=[os.path.join(REF_SSIM, s) for s in SSIM_SOURCES],
+        extra_cflags=["-O3"],
+        extra_cuda_cflags=["-O3", "--maxrregcount=32", "--use_fast_math", "-gencode", "arch=compute_100a,code=sm_100a"],
+        build_directory=out,
+        verbose=not quiet,
+        is_python_module=True,
+    )
+    import shutil
+    for f in os.listdir(out):
+        if f.startswith(SSIM_NAME) and f.endswith(".so"):
+            shutil.copy2(os.path.join(out, f), os.path.join(OUT, f))
+    return so_path(SSIM_NAME)
+
+
+def _load(name: str):
+    p = so_path(name)
     if p is None:
         return None
     import torch  # noqa: F401  (registers the ATen symbols the extension links against)
-    spec = importlib.util.spec_from_file_location(NAME, p)
+    spec = importlib.util.spec_from_file_location(name, p)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
 
 
+def load():
+    """Import the prebuilt reference module (needs torch; used on the GPU box). Returns None if absent."""
+    return _load(NAME)
+
+
+def load_ssim():
+    """Import the prebuilt reference fused_ssim_cuda module (fusedssim, fusedssim_backward, fusedl1ssim_loss,
+    fusedl1ssim_loss_backward). Returns None if absent."""
+    return _load(SSIM_NAME)
+
+
 if __name__ == "__main__":
     print(build(quiet="-q" in sys.argv))
+    print(build_ssim(quiet="-q" in sys.argv))

@@ -865,3 +865,132 @@ void SUF(orc_adam_chunk)(REAL* param, const REAL* grad, REAL* m, REAL* v2, const
         m[p] = e1; v2[p] = e2;
     }
 }
+
+/* ---- fused L1 + SSIM loss (next row) ---------------------------------------
+ * fused_ssim/ssim.cu:64-274 (ssim map + partial derivatives), :277-437 (backward), :528-712 and
+ * :719-850 (the L1 + SSIM loss variants).  11-tap Gaussian (sigma 1.5, the constants of ssim.cu:12-24),
+ * zero padding, separable: horizontal pass first, symmetric pairs from the centre outwards then the
+ * centre tap (ssim.cu:135-160), vertical pass the same way (:216-240).  Images are [B,CH,H,W]. */
+#ifndef ORC_SSIM_CONSTS
+#define ORC_SSIM_CONSTS
+static const float ORC_GAUSS11[11] = { 0.001028380123898387f, 0.0075987582094967365f, 0.036000773310661316f,
+    0.10936068743467331f, 0.21300552785396576f, 0.26601171493530273f, 0.21300552785396576f,
+    0.10936068743467331f, 0.036000773310661316f, 0.0075987582094967365f, 0.001028380123898387f };
+#endif
+
+static inline REAL SUF(pix0)(const REAL* plane, int H, int W, int y, int x)
+{
+    return (x < 0 || x >= W || y < 0 || y >= H) ? (REAL)0 : plane[(size_t)y * W + x];
+}
+
+/* l1_mode 0: map = ssim (ssim.cu:251-254); 1: map = w (1 - ssim) + (1 - w) |x - y| (ssim.cu:586-588,691).
+ * dm_* may be NULL (train = false). */
+void SUF(orc_ssim_forward)(const REAL* img1, const REAL* img2, int B, int CH, int H, int W, REAL C1, REAL C2,
+                           int l1_mode, REAL ssim_weight, REAL* map, REAL* dm_dmu1, REAL* dm_dsigma1_sq,
+                           REAL* dm_dsigma12)
+{
+    const size_t np = (size_t)H * W;
+#pragma omp parallel for schedule(static)
+    for (int pc = 0; pc < B * CH; pc++) {
+        const REAL* X = img1 + (size_t)pc * np;
+        const REAL* Y = img2 + (size_t)pc * np;
+        REAL* hx = (REAL*)malloc(sizeof(REAL) * 5 * (size_t)(H + 10) * W);   /* horizontal sums for rows -5..H+4 */
+        for (int yy = 0; yy < H + 10; yy++) for (int x = 0; x < W; x++) {
+            int y = yy - 5;
+            REAL s[5] = { 0, 0, 0, 0, 0 };
+            for (int d = 1; d <= 5; d++) {
+                REAL w = (REAL)ORC_GAUSS11[5 - d];
+                REAL xl = SUF(pix0)(X, H, W, y, x - d), yl = SUF(pix0)(Y, H, W, y, x - d);
+                REAL xr = SUF(pix0)(X, H, W, y, x + d), yr = SUF(pix0)(Y, H, W, y, x + d);
+                s[0] += (xl + xr) * w;
+                s[1] += ((xl * xl) + (xr * xr)) * w;
+                s[2] += (yl + yr) * w;
+                s[3] += ((yl * yl) + (yr * yr)) * w;
+                s[4] += ((xl * yl) + (xr * yr)) * w;
+            }
+            REAL cx = SUF(pix0)(X, H, W, y, x), cy = SUF(pix0)(Y, H, W, y, x), wc = (REAL)ORC_GAUSS11[5];
+            s[0] += cx * wc; s[1] += (cx * cx) * wc; s[2] += cy * wc; s[3] += (cy * cy) * wc; s[4] += (cx * cy) * wc;
+            for (int k = 0; k < 5; k++) hx[((size_t)yy * W + x) * 5 + k] = s[k];
+        }
+        for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
+            REAL o[5] = { 0, 0, 0, 0, 0 };
+            for (int d = 1; d <= 5; d++) {
+                REAL w = (REAL)ORC_GAUSS11[5 - d];
+                const REAL* top = hx + ((size_t)(y + 5 - d) * W + x) * 5;
+                const REAL* bot = hx + ((size_t)(y + 5 + d) * W + x) * 5;
+                for (int k = 0; k < 5; k++) o[k] += (top[k] + bot[k]) * w;
+            }
+            const REAL* ctr = hx + ((size_t)(y + 5) * W + x) * 5;
+            for (int k = 0; k < 5; k++) o[k] += ctr[k] * (REAL)ORC_GAUSS11[5];
+            REAL mu1 = o[0], mu2 = o[2];
+            REAL mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2;
+            REAL sigma1_sq = o[1] - mu1_sq, sigma2_sq = o[3] - mu2_sq, sigma12 = o[4] - mu1 * mu2;
+            REAL A = mu1_sq + mu2_sq + C1, Bv = sigma1_sq + sigma2_sq + C2;
+            REAL Cv = (REAL)2 * mu1 * mu2 + C1, Dv = (REAL)2 * sigma12 + C2;
+            REAL val = (Cv * Dv) / (A * Bv);
+            size_t gi = (size_t)pc * np + (size_t)y * W + x;
+            if (l1_mode) {
+                REAL l1 = FABS(X[(size_t)y * W + x] - Y[(size_t)y * W + x]);
+                map[gi] = ssim_weight * ((REAL)1 - val) + ((REAL)1 - ssim_weight) * l1;
+            } else {
+                map[gi] = val;
+            }
+            if (dm_dmu1) {
+                dm_dmu1[gi] = (mu2 * (REAL)2 * Dv) / (A * Bv) - (mu2 * (REAL)2 * Cv) / (A * Bv)
+                            - (mu1 * (REAL)2 * Cv * Dv) / (A * A * Bv) + (mu1 * (REAL)2 * Cv * Dv) / (A * Bv * Bv);
+                dm_dsigma1_sq[gi] = (-Cv * Dv) / (A * Bv * Bv);
+                dm_dsigma12[gi] = ((REAL)2 * Cv) / (A * Bv);
+            }
+        }
+        free(hx);
+    }
+}
+
+/* dL/dimg1 from dL/dmap and the saved partials: each partial x chain is filtered with the same separable
+ * Gaussian, then  dL/dpix = sum0 + 2 p1 sum1 + p2 sum2  (ssim.cu:417-424).  l1_mode 1 scales the partials by
+ * -ssim_weight and adds (1 - w) sign(p1 - p2) chain (ssim.cu:775-779,833-844). */
+void SUF(orc_ssim_backward)(const REAL* img1, const REAL* img2, const REAL* dL_dmap, const REAL* dm_dmu1,
+                            const REAL* dm_dsigma1_sq, const REAL* dm_dsigma12, int B, int CH, int H, int W,
+                            int l1_mode, REAL ssim_weight, REAL* dL_dimg1)
+{
+    const size_t np = (size_t)H * W;
+    const REAL scale = l1_mode ? -ssim_weight : (REAL)1;
+#pragma omp parallel for schedule(static)
+    for (int pc = 0; pc < B * CH; pc++) {
+        const REAL* ch = dL_dmap + (size_t)pc * np;
+        const REAL* m[3] = { dm_dmu1 + (size_t)pc * np, dm_dsigma1_sq + (size_t)pc * np, dm_dsigma12 + (size_t)pc * np };
+        REAL* hx = (REAL*)malloc(sizeof(REAL) * 3 * (size_t)(H + 10) * W);
+        for (int yy = 0; yy < H + 10; yy++) for (int x = 0; x < W; x++) {
+            int y = yy - 5;
+            for (int k = 0; k < 3; k++) {
+                REAL acc = 0;
+                for (int d = 1; d <= 5; d++) {
+                    REAL l = scale * SUF(pix0)(m[k], H, W, y, x - d) * SUF(pix0)(ch, H, W, y, x - d);
+                    REAL r = scale * SUF(pix0)(m[k], H, W, y, x + d) * SUF(pix0)(ch, H, W, y, x + d);
+                    acc += (l + r) * (REAL)ORC_GAUSS11[5 - d];
+                }
+                acc += (scale * SUF(pix0)(m[k], H, W, y, x) * SUF(pix0)(ch, H, W, y, x)) * (REAL)ORC_GAUSS11[5];
+                hx[((size_t)yy * W + x) * 3 + k] = acc;
+            }
+        }
+        for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
+            REAL s[3] = { 0, 0, 0 };
+            for (int d = 1; d <= 5; d++) {
+                const REAL* top = hx + ((size_t)(y + 5 - d) * W + x) * 3;
+                const REAL* bot = hx + ((size_t)(y + 5 + d) * W + x) * 3;
+                for (int k = 0; k < 3; k++) s[k] += (top[k] + bot[k]) * (REAL)ORC_GAUSS11[5 - d];
+            }
+            const REAL* ctr = hx + ((size_t)(y + 5) * W + x) * 3;
+            for (int k = 0; k < 3; k++) s[k] += ctr[k] * (REAL)ORC_GAUSS11[5];
+            size_t gi = (size_t)pc * np + (size_t)y * W + x;
+            REAL p1 = img1[gi], p2 = img2[gi];
+            REAL g = s[0] + ((REAL)2 * p1) * s[1] + p2 * s[2];
+            if (l1_mode) {
+                REAL sg = (p1 == p2) ? (REAL)0 : (p1 > p2 ? (REAL)1 : (REAL)-1);
+                g += ((REAL)1 - ssim_weight) * sg * ch[(size_t)y * W + x];
+            }
+            dL_dimg1[gi] = g;
+        }
+        free(hx);
+    }
+}
