@@ -9,7 +9,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblitegs_b200.so")
+LIB_PATH = os.environ.get("LITEGS_B200_LIB") or os.path.join(_HERE, "liblitegs_b200.so")   # env: A/B builds only
 
 _P, _I, _D, _Z, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_size_t, ctypes.c_float
 

@@ -3,24 +3,32 @@
 // replaces fused_ssim/ssim.cu:64-274, 277-437 (SSIM), 528-712, 719-850 (L1 + SSIM loss) and their hosts :444-524, 855-942.
 //
 // Same maths as the reference (11-tap sigma-1.5 Gaussian, zero padding, separable, per channel; the partial derivatives
-// dm/dmu1, dm/dsigma1^2, dm/dsigma12 are saved by the forward and filtered again by the backward), different schedule:
-// a CTA owns a 64 x 32 output tile.  The (64+10) x (32+10) input window of both images is staged in shared memory once;
-// the horizontal pass gives every lane a strip of 8 adjacent outputs of ONE row (18 loads feed 8 x 5 x 11 FMAs, the
-// products x^2, y^2, xy are formed once per pixel instead of once per tap; lanes of a warp walk consecutive rows with an
-// odd row stride, so the strip loads are bank-conflict free); the vertical pass gives every thread a strip of 8 outputs
-// of one column (18 x 5 loads, lanes on consecutive columns).  That is ~30 shared-memory accesses per output instead of
-// the ~130 of a thread-per-pixel schedule, which is what bounds this filter on B200 (the data is small: 20 B/pixel).
+// dm/dmu1, dm/dsigma1^2, dm/dsigma12 are saved by the forward and filtered again by the backward), different schedule.
+// The reference stages a 26x26 window per 16x16 tile and keeps a 5-channel intermediate image in shared memory; that costs
+// ~130 shared-memory accesses and ~440 issued instructions per output and caps occupancy at 25 % on B200 (first version of
+// this file, profiles/ncu_ssim_r1_tiled_first_version.txt).  Here a CTA is a band of 128 columns x 32 rows and every thread streams DOWN
+// one column:
+//   * vertical pass in registers, straight from global memory (coalesced across the warp, 11 rows of loads in flight):
+//     each incoming row is scattered into the 11 pending output rows of a register ring (statically indexed: the row loop
+//     is unrolled by 11), so no intermediate image exists;
+//   * when a ring slot completes, the 4 vertically filtered moments of that row go to a double-buffered 2 KB row buffer
+//     (one __syncthreads per row) and each thread finishes its own pixel with the horizontal pass (44 conflict-free LDS);
+//   * 4 moments instead of 5: SSIM only needs sigma1^2 + sigma2^2, so x^2 + y^2 is filtered as ONE image.
+// ~190 instructions and ~48 shared-memory accesses per output, ~100 registers, 2 KB of shared memory per CTA.
 // The loss map itself is optional: the training path only needs its mean, so the kernel can emit one partial sum per
 // CTA instead (summed on the host side in a fixed order -> deterministic).
 #include "common.cuh"
 
 namespace {
 
-constexpr int TX = 64, TY = 32, HALO = 5;
-constexpr int IX = TX + 2 * HALO, IY = TY + 2 * HALO;       // 74 x 42 input window
-constexpr int ISTRIDE = IX + 1;                              // 75: odd, lanes on consecutive rows hit distinct banks
-constexpr int STRIP = 8;
-constexpr int THREADS = 256;
+constexpr int CT = 128;                 // threads = columns per CTA (incl. 2 x 5 halo columns)
+constexpr int HALO = 5;
+constexpr int CO = CT - 2 * HALO;       // 118 output columns per CTA
+#ifndef LGS_SSIM_BH
+#define LGS_SSIM_BH 32
+#endif
+constexpr int BH = LGS_SSIM_BH;         // output rows per CTA
+constexpr int RIN = BH + 2 * HALO;      // input rows a thread streams
 
 __device__ __forceinline__ float gauss(int k)
 {
@@ -31,205 +39,205 @@ __device__ __forceinline__ float gauss(int k)
     return G[k];
 }
 
-// out[j] = sum_k g[k] * in[j + k]   for STRIP outputs from STRIP + 10 inputs
-__device__ __forceinline__ void conv_strip(const float (&in)[STRIP + 10], float (&out)[STRIP])
+__device__ __forceinline__ float rcp_approx(float x)
 {
-#pragma unroll
-    for (int j = 0; j < STRIP; j++) {
-        float acc = gauss(0) * in[j];
-#pragma unroll
-        for (int k = 1; k < 11; k++) acc = fmaf(gauss(k), in[j + k], acc);
-        out[j] = acc;
-    }
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
-
-__device__ __forceinline__ void load_window(const float* __restrict__ plane, int H, int W, int x0, int y0, float* __restrict__ s)
-{
-    for (int i = threadIdx.x; i < IY * IX; i += THREADS) {
-        int ly = i / IX, lx = i - ly * IX;
-        int gy = y0 - HALO + ly, gx = x0 - HALO + lx;
-        float v = 0.0f;
-        if (gx >= 0 && gx < W && gy >= 0 && gy < H) v = plane[(size_t)gy * W + gx];
-        s[ly * ISTRIDE + lx] = v;
-    }
-}
-
-template <int NCH>
-struct HBuf { float v[NCH][IY][TX]; };
 
 // L1: loss map w (1 - ssim) + (1 - w) |x - y| instead of the ssim map.   TRAIN: write the three partials.
 template <bool L1, bool TRAIN>
-__global__ void __launch_bounds__(THREADS) ssim_forward_kernel(const float* __restrict__ img1, const float* __restrict__ img2, int H, int W,
-                                                               float C1, float C2, float ssim_weight, float* __restrict__ map,
-                                                               float* __restrict__ dm_dmu1, float* __restrict__ dm_dsigma1_sq,
-                                                               float* __restrict__ dm_dsigma12, float* __restrict__ block_sums)
+__global__ void __launch_bounds__(CT) ssim_forward_kernel(const float* __restrict__ img1, const float* __restrict__ img2, int H, int W,
+                                                          float C1, float C2, float ssim_weight, float* __restrict__ map,
+                                                          float* __restrict__ dm_dmu1, float* __restrict__ dm_dsigma1_sq,
+                                                          float* __restrict__ dm_dsigma12, float* __restrict__ block_sums)
 {
-    extern __shared__ float smem[];
-    float* sX = smem;
-    float* sY = smem + IY * ISTRIDE;
-    HBuf<5>& hb = *reinterpret_cast<HBuf<5>*>(smem + 2 * IY * ISTRIDE);
+    constexpr int NM = 4;                                  // x, y, x^2 + y^2, x y
+    __shared__ float rowbuf[2][NM][CT];
     const size_t plane = (size_t)blockIdx.z * H * W;
-    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    load_window(img1 + plane, H, W, x0, y0, sX);
-    load_window(img2 + plane, H, W, x0, y0, sY);
-    __syncthreads();
-    // horizontal pass: warp w owns the strip of columns [8w, 8w+8), lanes walk the rows
-    for (int row = lane; row < IY; row += 32) {
-        float a[STRIP + 10], b[STRIP + 10], p[STRIP + 10], o[STRIP];
+    const float* X = img1 + plane;
+    const float* Y = img2 + plane;
+    const int t = threadIdx.x;
+    const int gx = (int)blockIdx.x * CO - HALO + t;        // this thread's column
+    const int y0 = (int)blockIdx.y * BH;                   // first output row
+    const bool col_in = gx >= 0 && gx < W;
+    const bool col_out = t >= HALO && t < CT - HALO && gx < W;
+    float acc[11][NM];
+    float l1v[11];
 #pragma unroll
-        for (int j = 0; j < STRIP + 10; j++) { a[j] = sX[row * ISTRIDE + w * STRIP + j]; b[j] = sY[row * ISTRIDE + w * STRIP + j]; }
-        conv_strip(a, o);
+    for (int i = 0; i < 11; i++) {
+        l1v[i] = 0.0f;
 #pragma unroll
-        for (int j = 0; j < STRIP; j++) hb.v[0][row][w * STRIP + j] = o[j];
-        conv_strip(b, o);
-#pragma unroll
-        for (int j = 0; j < STRIP; j++) hb.v[2][row][w * STRIP + j] = o[j];
-#pragma unroll
-        for (int j = 0; j < STRIP + 10; j++) p[j] = a[j] * a[j];
-        conv_strip(p, o);
-#pragma unroll
-        for (int j = 0; j < STRIP; j++) hb.v[1][row][w * STRIP + j] = o[j];
-#pragma unroll
-        for (int j = 0; j < STRIP + 10; j++) p[j] = b[j] * b[j];
-        conv_strip(p, o);
-#pragma unroll
-        for (int j = 0; j < STRIP; j++) hb.v[3][row][w * STRIP + j] = o[j];
-#pragma unroll
-        for (int j = 0; j < STRIP + 10; j++) p[j] = a[j] * b[j];
-        conv_strip(p, o);
-#pragma unroll
-        for (int j = 0; j < STRIP; j++) hb.v[4][row][w * STRIP + j] = o[j];
+        for (int m = 0; m < NM; m++) acc[i][m] = 0.0f;
     }
-    __syncthreads();
-    // vertical pass: thread = (column, strip of 8 rows)
-    const int cx = t & (TX - 1), ys = (t >> 6) * STRIP;
-    float mom[5][STRIP];
-#pragma unroll
-    for (int k = 0; k < 5; k++) {
-        float in[STRIP + 10];
-#pragma unroll
-        for (int j = 0; j < STRIP + 10; j++) in[j] = hb.v[k][ys + j][cx];
-        conv_strip(in, mom[k]);
-    }
-    const int gx = x0 + cx;
     float lsum = 0.0f;
+    int emitted = 0;
+    for (int r0 = 0; r0 < RIN; r0 += 11) {
+        float xs[11], ys[11];
 #pragma unroll
-    for (int j = 0; j < STRIP; j++) {
-        const int gy = y0 + ys + j;
-        if (gx < W && gy < H) {
-            float mu1 = mom[0][j], mu2 = mom[2][j];
-            float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2;
-            float sigma1_sq = mom[1][j] - mu1_sq, sigma2_sq = mom[3][j] - mu2_sq, sigma12 = mom[4][j] - mu1 * mu2;
-            float A = mu1_sq + mu2_sq + C1, B = sigma1_sq + sigma2_sq + C2;
-            float C = 2.0f * mu1 * mu2 + C1, D = 2.0f * sigma12 + C2;
-            float iAB = 1.0f / (A * B);
-            float val = (C * D) * iAB;
-            float out = val;
-            if (L1) {
-                float l1 = fabsf(sX[(ys + j + HALO) * ISTRIDE + cx + HALO] - sY[(ys + j + HALO) * ISTRIDE + cx + HALO]);
-                out = ssim_weight * (1.0f - val) + (1.0f - ssim_weight) * l1;
-            }
-            const size_t gi = plane + (size_t)gy * W + gx;
-            if (map != nullptr) map[gi] = out;
-            lsum += out;
-            if (TRAIN) {
-                // fused_ssim/ssim.cu:258-268 with the common factor 1/(A B) pulled out
-                dm_dmu1[gi] = 2.0f * iAB * (mu2 * (D - C) + mu1 * C * D * (1.0f / B - 1.0f / A));
-                dm_dsigma1_sq[gi] = -(C * D) * iAB / B;
-                dm_dsigma12[gi] = 2.0f * C * iAB;
+        for (int i = 0; i < 11; i++) {                     // 11 rows of loads in flight
+            const int gy = y0 - HALO + r0 + i;
+            const bool in = col_in && r0 + i < RIN && gy >= 0 && gy < H;
+            xs[i] = in ? X[(size_t)gy * W + gx] : 0.0f;
+            ys[i] = in ? Y[(size_t)gy * W + gx] : 0.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < 11; i++) {
+            if (r0 + i < RIN) {                            // uniform across the CTA
+                const float x = xs[i], y = ys[i];
+                const float q[NM] = { x, y, fmaf(x, x, y * y), x * y };
+                if (L1) l1v[i] = fabsf(x - y);
+                // input row r = r0 + i feeds output rows r - j with tap j; output row o lives in slot o % 11
+#pragma unroll
+                for (int j = 0; j < 11; j++) {
+                    const int slot = (i - j + 11) % 11;
+#pragma unroll
+                    for (int m = 0; m < NM; m++) acc[slot][m] = fmaf(gauss(j), q[m], acc[slot][m]);
+                }
+                // slot (i + 1) % 11 now holds output row o = r - 10: complete if o >= 0, otherwise the partial sums of a
+                // row above the band, to be discarded; either way the slot restarts at zero for output row r + 1
+                float done[NM];
+#pragma unroll
+                for (int m = 0; m < NM; m++) { done[m] = acc[(i + 1) % 11][m]; acc[(i + 1) % 11][m] = 0.0f; }
+                if (r0 + i >= 10) {
+                    const int buf = emitted & 1;
+#pragma unroll
+                    for (int m = 0; m < NM; m++) rowbuf[buf][m][t] = done[m];
+                    __syncthreads();
+                    const int gy = y0 + r0 + i - 10;
+                    if (col_out && gy < H) {
+                        float mom[NM];
+#pragma unroll
+                        for (int m = 0; m < NM; m++) {
+                            float a = gauss(0) * rowbuf[buf][m][t - HALO];
+#pragma unroll
+                            for (int k = 1; k < 11; k++) a = fmaf(gauss(k), rowbuf[buf][m][t - HALO + k], a);
+                            mom[m] = a;
+                        }
+                        const float mu1 = mom[0], mu2 = mom[1];
+                        const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2;
+                        const float A = mu1_sq + mu2_sq + C1;
+                        const float B = (mom[2] - mu1_sq - mu2_sq) + C2;           // sigma1^2 + sigma2^2 + C2
+                        const float sigma12 = mom[3] - mu1 * mu2;
+                        const float C = 2.0f * mu1 * mu2 + C1, D = 2.0f * sigma12 + C2;
+                        const float iA = rcp_approx(A), iB = rcp_approx(B);       // MUFU.RCP, 1 ulp: A, B >= C1, C2 > 0
+                        const float iAB = iA * iB;
+                        const float val = (C * D) * iAB;
+                        float out = val;
+                        if (L1) out = ssim_weight * (1.0f - val) + (1.0f - ssim_weight) * l1v[(i + 6) % 11];   // centre row r - 5
+                        const size_t gi = plane + (size_t)gy * W + gx;
+                        if (map != nullptr) map[gi] = out;
+                        lsum += out;
+                        if (TRAIN) {
+                            // fused_ssim/ssim.cu:258-268 with the common factor 1/(A B) pulled out
+                            dm_dmu1[gi] = 2.0f * iAB * (mu2 * (D - C) + mu1 * C * D * (iB - iA));
+                            dm_dsigma1_sq[gi] = -(C * D) * iAB * iB;
+                            dm_dsigma12[gi] = 2.0f * C * iAB;
+                        }
+                    }
+                    emitted++;
+                }
             }
         }
     }
     if (block_sums != nullptr) {
-        __shared__ float s_part[THREADS / 32];
+        __shared__ float s_part[CT / 32];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-        if (lane == 0) s_part[w] = lsum;
+        if ((t & 31) == 0) s_part[t >> 5] = lsum;
         __syncthreads();
         if (t == 0) {
             float s = 0.0f;
 #pragma unroll
-            for (int k = 0; k < THREADS / 32; k++) s += s_part[k];
+            for (int k = 0; k < CT / 32; k++) s += s_part[k];
             block_sums[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = s;
         }
     }
 }
 
-// dL_dmap == nullptr: uniform upstream gradient `chain` (loss = mean of the map)
-template <bool L1>
-__global__ void __launch_bounds__(THREADS) ssim_backward_kernel(const float* __restrict__ img1, const float* __restrict__ img2,
-                                                                const float* __restrict__ dL_dmap, float chain,
-                                                                const float* __restrict__ dm_dmu1, const float* __restrict__ dm_dsigma1_sq,
-                                                                const float* __restrict__ dm_dsigma12, int H, int W, float ssim_weight,
-                                                                float* __restrict__ dL_dimg1)
+// UNIFORM: dL_dmap == nullptr, the upstream gradient is the constant `chain` (loss = mean of the map): one load stream
+// and 22 registers fewer than with a per-pixel upstream gradient
+template <bool L1, bool UNIFORM>
+__global__ void __launch_bounds__(CT) ssim_backward_kernel(const float* __restrict__ img1, const float* __restrict__ img2,
+                                                           const float* __restrict__ dL_dmap, float chain,
+                                                           const float* __restrict__ dm_dmu1, const float* __restrict__ dm_dsigma1_sq,
+                                                           const float* __restrict__ dm_dsigma12, int H, int W, float ssim_weight,
+                                                           float* __restrict__ dL_dimg1)
 {
-    extern __shared__ float smem[];
-    float* sM[3] = { smem, smem + IY * ISTRIDE, smem + 2 * IY * ISTRIDE };
-    HBuf<3>& hb = *reinterpret_cast<HBuf<3>*>(smem + 3 * IY * ISTRIDE);
+    constexpr int NM = 3;
+    __shared__ float rowbuf[2][NM][CT];
     const size_t plane = (size_t)blockIdx.z * H * W;
-    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int t = threadIdx.x;
+    const int gx = (int)blockIdx.x * CO - HALO + t;
+    const int y0 = (int)blockIdx.y * BH;
+    const bool col_in = gx >= 0 && gx < W;
+    const bool col_out = t >= HALO && t < CT - HALO && gx < W;
     const float scale = L1 ? -ssim_weight : 1.0f;                  // d loss / d ssim  (fused_ssim/ssim.cu:775-779)
-    for (int i = t; i < IY * IX; i += THREADS) {
-        int ly = i / IX, lx = i - ly * IX;
-        int gy = y0 - HALO + ly, gx = x0 - HALO + lx;
-        float m0 = 0.0f, m1 = 0.0f, m2 = 0.0f;
-        if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
-            const size_t gi = plane + (size_t)gy * W + gx;
-            const float c = scale * (dL_dmap != nullptr ? dL_dmap[gi] : chain);
-            m0 = dm_dmu1[gi] * c; m1 = dm_dsigma1_sq[gi] * c; m2 = dm_dsigma12[gi] * c;
+    float acc[11][NM];
+    float cv[UNIFORM ? 1 : 11];                                     // upstream gradient of the last 11 input rows
+#pragma unroll
+    for (int i = 0; i < 11; i++) {
+        if (!UNIFORM) cv[i] = 0.0f;
+#pragma unroll
+        for (int m = 0; m < NM; m++) acc[i][m] = 0.0f;
+    }
+    int emitted = 0;
+    for (int r0 = 0; r0 < RIN; r0 += 11) {
+        float q[11][NM], cn[UNIFORM ? 1 : 11];
+#pragma unroll
+        for (int i = 0; i < 11; i++) {
+            const int gy = y0 - HALO + r0 + i;
+            const bool in = col_in && r0 + i < RIN && gy >= 0 && gy < H;
+            const size_t gi = plane + (size_t)(in ? gy : 0) * W + (in ? gx : 0);
+            const float c = UNIFORM ? chain : (in ? dL_dmap[gi] : 0.0f);
+            if (!UNIFORM) cn[i] = c;
+            q[i][0] = in ? dm_dmu1[gi] * (scale * c) : 0.0f;
+            q[i][1] = in ? dm_dsigma1_sq[gi] * (scale * c) : 0.0f;
+            q[i][2] = in ? dm_dsigma12[gi] * (scale * c) : 0.0f;
         }
-        sM[0][ly * ISTRIDE + lx] = m0; sM[1][ly * ISTRIDE + lx] = m1; sM[2][ly * ISTRIDE + lx] = m2;
-    }
-    __syncthreads();
-    for (int row = lane; row < IY; row += 32) {
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-            float a[STRIP + 10], o[STRIP];
+        for (int i = 0; i < 11; i++) {
+            if (r0 + i < RIN) {
+                if (!UNIFORM) cv[i] = cn[i];                        // slot i is free: its row (r - 11) was last used 6 rows ago
 #pragma unroll
-            for (int j = 0; j < STRIP + 10; j++) a[j] = sM[k][row * ISTRIDE + w * STRIP + j];
-            conv_strip(a, o);
+                for (int j = 0; j < 11; j++) {
+                    const int slot = (i - j + 11) % 11;
 #pragma unroll
-            for (int j = 0; j < STRIP; j++) hb.v[k][row][w * STRIP + j] = o[j];
-        }
-    }
-    __syncthreads();
-    const int cx = t & (TX - 1), ys = (t >> 6) * STRIP;
-    float s[3][STRIP];
+                    for (int m = 0; m < NM; m++) acc[slot][m] = fmaf(gauss(j), q[i][m], acc[slot][m]);
+                }
+                float done[NM];
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-        float in[STRIP + 10];
+                for (int m = 0; m < NM; m++) { done[m] = acc[(i + 1) % 11][m]; acc[(i + 1) % 11][m] = 0.0f; }
+                if (r0 + i >= 10) {
+                    const int buf = emitted & 1;
 #pragma unroll
-        for (int j = 0; j < STRIP + 10; j++) in[j] = hb.v[k][ys + j][cx];
-        conv_strip(in, s[k]);
-    }
-    const int gx = x0 + cx;
+                    for (int m = 0; m < NM; m++) rowbuf[buf][m][t] = done[m];
+                    __syncthreads();
+                    const int gy = y0 + r0 + i - 10;
+                    if (col_out && gy < H) {
+                        float s[NM];
 #pragma unroll
-    for (int j = 0; j < STRIP; j++) {
-        const int gy = y0 + ys + j;
-        if (gx < W && gy < H) {
-            const size_t gi = plane + (size_t)gy * W + gx;
-            const float p1 = img1[gi], p2 = img2[gi];
-            float g = s[0][j] + (2.0f * p1) * s[1][j] + p2 * s[2][j];             // fused_ssim/ssim.cu:417-421
-            if (L1) {
-                const float c = dL_dmap != nullptr ? dL_dmap[gi] : chain;
-                const float sg = (p1 == p2) ? 0.0f : copysignf(1.0f, p1 - p2);      // fused_ssim/ssim.cu:840-841
-                g += (1.0f - ssim_weight) * sg * c;
+                        for (int m = 0; m < NM; m++) {
+                            float a = gauss(0) * rowbuf[buf][m][t - HALO];
+#pragma unroll
+                            for (int k = 1; k < 11; k++) a = fmaf(gauss(k), rowbuf[buf][m][t - HALO + k], a);
+                            s[m] = a;
+                        }
+                        const size_t gi = plane + (size_t)gy * W + gx;
+                        const float p1 = img1[gi], p2 = img2[gi];
+                        float g = s[0] + (2.0f * p1) * s[1] + p2 * s[2];                   // fused_ssim/ssim.cu:417-421
+                        if (L1) {
+                            const float sg = (p1 == p2) ? 0.0f : copysignf(1.0f, p1 - p2);  // fused_ssim/ssim.cu:840-841
+                            g += (1.0f - ssim_weight) * sg * (UNIFORM ? chain : cv[UNIFORM ? 0 : (i + 6) % 11]);   // upstream of the centre row r - 5
+                        }
+                        dL_dimg1[gi] = g;
+                    }
+                    emitted++;
+                }
             }
-            dL_dimg1[gi] = g;
         }
     }
-}
-
-constexpr size_t FWD_SMEM = (2 * IY * ISTRIDE) * sizeof(float) + sizeof(HBuf<5>);
-constexpr size_t BWD_SMEM = (3 * IY * ISTRIDE) * sizeof(float) + sizeof(HBuf<3>);
-
-template <typename K>
-int opt_in_smem(K kernel, size_t bytes)
-{
-    LGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    return LGS_OK;
 }
 
 }  // namespace
@@ -238,7 +246,7 @@ int opt_in_smem(K kernel, size_t bytes)
 extern "C" int lgs_ssim_num_block_sums(int B, int CH, int H, int W, int* count)
 {
     LGS_REQUIRE(B >= 1 && CH >= 1 && H >= 1 && W >= 1 && count != nullptr, "ssim_num_block_sums: bad arguments");
-    *count = B * CH * ((H + TY - 1) / TY) * ((W + TX - 1) / TX);
+    *count = B * CH * ((H + BH - 1) / BH) * ((W + CO - 1) / CO);
     return LGS_OK;
 }
 
@@ -253,14 +261,9 @@ extern "C" int lgs_ssim_forward(const float* img1, const float* img2, int B, int
     LGS_REQUIRE(!train || (dm_dsigma1_sq != nullptr && dm_dsigma12 != nullptr), "ssim_forward: the three partial maps come together");
     LGS_REQUIRE(map != nullptr || block_sums != nullptr || train, "ssim_forward: nothing to compute");
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid((W + TX - 1) / TX, (H + TY - 1) / TY, B * CH);
-#define FWD(L, T)                                                                                                              \
-    do {                                                                                                                       \
-        static int once = opt_in_smem(ssim_forward_kernel<L, T>, FWD_SMEM);                                                    \
-        if (once != LGS_OK) return once;                                                                                       \
-        ssim_forward_kernel<L, T><<<grid, THREADS, FWD_SMEM, st>>>(img1, img2, H, W, C1, C2, ssim_weight, map, dm_dmu1, dm_dsigma1_sq, \
-                                                                  dm_dsigma12, block_sums);                                    \
-    } while (0)
+    dim3 grid((W + CO - 1) / CO, (H + BH - 1) / BH, B * CH);
+#define FWD(L, T) ssim_forward_kernel<L, T><<<grid, CT, 0, st>>>(img1, img2, H, W, C1, C2, ssim_weight, map, dm_dmu1, dm_dsigma1_sq, \
+                                                                 dm_dsigma12, block_sums)
     if (l1_mode) { if (train) FWD(true, true); else FWD(true, false); }
     else { if (train) FWD(false, true); else FWD(false, false); }
 #undef FWD
@@ -276,15 +279,11 @@ extern "C" int lgs_ssim_backward(const float* img1, const float* img2, const flo
     LGS_REQUIRE(img1 && img2 && dm_dmu1 && dm_dsigma1_sq && dm_dsigma12 && dL_dimg1, "ssim_backward: null tensor");
     LGS_REQUIRE((size_t)B * CH <= 65535, "ssim_backward: B*CH = %d exceeds the grid z limit", B * CH);
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid((W + TX - 1) / TX, (H + TY - 1) / TY, B * CH);
-#define BWD(L)                                                                                                                 \
-    do {                                                                                                                       \
-        static int once = opt_in_smem(ssim_backward_kernel<L>, BWD_SMEM);                                                      \
-        if (once != LGS_OK) return once;                                                                                       \
-        ssim_backward_kernel<L><<<grid, THREADS, BWD_SMEM, st>>>(img1, img2, dL_dmap, uniform_chain, dm_dmu1, dm_dsigma1_sq,   \
-                                                                dm_dsigma12, H, W, ssim_weight, dL_dimg1);                     \
-    } while (0)
-    if (l1_mode) BWD(true); else BWD(false);
+    dim3 grid((W + CO - 1) / CO, (H + BH - 1) / BH, B * CH);
+#define BWD(L, U) ssim_backward_kernel<L, U><<<grid, CT, 0, st>>>(img1, img2, dL_dmap, uniform_chain, dm_dmu1, dm_dsigma1_sq, dm_dsigma12, H, \
+                                                                  W, ssim_weight, dL_dimg1)
+    if (dL_dmap == nullptr) { if (l1_mode) BWD(true, true); else BWD(false, true); }
+    else { if (l1_mode) BWD(true, false); else BWD(false, false); }
 #undef BWD
     LGS_CHECK_LAUNCH("ssim_backward_kernel");
     return LGS_OK;
