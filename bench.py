@@ -312,11 +312,16 @@ def run_ours(args, rank, world, local_rank):
     g = torch.Generator(device="cpu").manual_seed(1)
     w_host = torch.randn((1, 3, H, W), generator=g)
     w = w_host.to(dev)
-    acc = lgs_dist.GradAccumulator(P)
+    # two gradient buffers: step k accumulates into buffer k % 2 while the all-reduce of step k-1 (NCCL, side stream)
+    # is still in flight -- the only cross-rank exchange of the path leaves the critical path (N > 1)
+    accs = [lgs_dist.GradAccumulator(P), lgs_dist.GradAccumulator(P)] if world > 1 else [lgs_dist.GradAccumulator(P)]
+    acc = accs[0]
+    step_no = {"k": 0}
     timer = StageTimer(); timer.install()
     launches = {"n": 0}
 
     acc_views = acc.grads()
+    acc_views_all = [a.grads() for a in accs]
     n_streams = max(1, args.streams) if args.level == "B" else 1
 
     def render_one_level_a(cam, weight):
@@ -339,19 +344,25 @@ def run_ours(args, rank, world, local_rank):
         CUDA streams, gradients accumulated into the dense buffer by the backward kernel) or the op-by-op level A."""
         if args.level == "B":
             return render.render_views(vpr, camera_fn, loss_fn, A[0], A[1], P["xyz"], P["scale"], P["rot"], P["sh_0"], P["sh_rest"],
-                                       P["opacity"], args.sh_degree, (H, W), pp, acc_views, n_streams=1 if serial else n_streams)
+                                       P["opacity"], args.sh_degree, (H, W), pp, acc_views_all[step_no["k"] % len(accs)],
+                                       n_streams=1 if serial else n_streams)
         return [render_one_level_a(camera_fn(j), loss_fn(j, None)) for j in range(vpr)]
 
     def step(serial=False):
-        acc.zero_()
+        a = accs[step_no["k"] % len(accs)] if args.level == "B" else acc
+        a.wait()                      # this buffer's previous all-reduce (two steps ago) must have landed
+        a.zero_()
         if args.level == "B":
             run_views(lambda j: cams[j], lambda j, img: (img * w).sum(), serial)
         else:
             run_views(lambda j: cams[j], lambda j, img: w, serial)
         if world > 1:
-            acc.all_reduce()
+            a.all_reduce(async_op=(args.level == "B"))
+        step_no["k"] += 1
 
     def barrier():
+        for a in accs:
+            a.wait()                  # every step's all-reduce is inside the timed region
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
@@ -368,6 +379,8 @@ def run_ours(args, rank, world, local_rank):
     e0.record()
     for _ in range(args.steps):
         step()
+    for a in accs:
+        a.wait()
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -425,10 +438,13 @@ def run_ours(args, rank, world, local_rank):
             return loss
 
         def e2e_step():
-            acc.zero_()
+            a = accs[step_no["k"] % len(accs)] if args.level == "B" else acc
+            a.wait()
+            a.zero_()
             out = run_views(e2e_camera, e2e_loss)
             if world > 1:
-                acc.all_reduce()
+                a.all_reduce()
+            step_no["k"] += 1
             torch.cuda.current_stream(dev).synchronize()          # the step's losses are on the host now
             if args.level == "A":
                 loss_host.copy_(torch.stack(out).reshape(-1))
@@ -511,7 +527,7 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": f"{args.gaussians} Gaussians (seed 0), {W}x{H}, sh_degree {args.sh_degree}, tile {args.tile}, "
-                               f"{vpr} views/rank/step (render_views) + dense grad accumulate" + (" + NCCL all-reduce" if world > 1 else ""),
+                               f"{vpr} views/rank/step (render_views) + dense grad accumulate" + (" + NCCL all-reduce of the step's buffer overlapped with the next step (2 buffers)" if world > 1 else ""),
                    "parallelism": f"dp{world} (views sharded, parameters replicated)", "level": args.level,
                    "l2": "inputs exceed L2 (236 MB of parameters streamed per view); no explicit flush",
                    "staging": args.staging or os.environ.get("LGS_STAGING", "default"), "streams": n_streams,
