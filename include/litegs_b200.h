@@ -221,13 +221,14 @@ int lgs_emit_pairs_u16(const float* packed_params, const int* offset, const unsi
  * replaces unpack_gradient + inv_2x2matrix_backward(+nan_to_num) + createCov2dDirectly_backward +
  * createTransformMatrix_backward + mvp_transform_backward + activate_backward (wrapper.py:481-524,588-592,404-407,
  * 190-193,278-285,820-845).  zero_outputs: 0 = assign compacted [..,A,S] outputs, 1 = clear them first,
- * 2 = ACCUMULATE into dense [..,C,S] gradient tensors at the source chunk (multi-view / data-parallel path). */
+ * 2 = ACCUMULATE into dense [..,C,S] gradient tensors at the source chunk (multi-view / data-parallel path).
+ * touched (f32[C], may be NULL) receives 1 at every visible chunk: the marks lgs_adam_step_dense consumes. */
 int lgs_project_backward(int sh_degree, const int64_t* visible_chunk_id, const int* visible_chunks_num,
                          const float* view_matrix, const float* proj_matrix, const float* position, const float* scale,
                          const float* rotation, const float* opacity, int C, int S, int A, int rest_dim, int img_h,
                          int img_w, int true_sigmoid_grad, const float* packed_grad, const float* grad_inv_scaler,
                          int zero_outputs, float* g_position, float* g_scale, float* g_rotation, float* g_sh_base,
-                         float* g_sh_rest, float* g_opacity, void* stream);
+                         float* g_sh_rest, float* g_opacity, float* touched, void* stream);
 
 /* ---- optimiser / statistics (next rows) ------------------------------------------------------ */
 

@@ -292,12 +292,13 @@ __global__ void project_backward_kernel(
     const float* __restrict__ rot, const float* __restrict__ opac, int C, int S, int A, int rest_dim, int H, int W,
     int true_sigmoid, int accumulate, const float* __restrict__ grad /*[A*S,12]*/, const float* __restrict__ inv_scaler,
     float* __restrict__ g_pos, float* __restrict__ g_scale, float* __restrict__ g_rot, float* __restrict__ g_sh0,
-    float* __restrict__ g_shr, float* __restrict__ g_opac)
+    float* __restrict__ g_shr, float* __restrict__ g_opac, float* __restrict__ touched)
 {
     const int a = blockIdx.x, s = threadIdx.x;
     if (a >= visible_num[0]) return;
     const size_t CS = (size_t)C * S, AS = (size_t)A * S;
     const size_t dst = (size_t)a * S + s, src = (size_t)chunk_ids[a] * S + s;
+    if (touched != nullptr && s == 0) touched[chunk_ids[a]] = 1.0f;     // chunk mark for the fused optimizer step
     constexpr int K = (DEG + 1) * (DEG + 1);
     const float sc = inv_scaler ? inv_scaler[0] : 1.0f;
     const float4* g4 = reinterpret_cast<const float4*>(grad + dst * LGS_GRAD_FLOATS);
@@ -428,7 +429,8 @@ extern "C" int lgs_project_backward(int sh_degree, const int64_t* visible_chunk_
                                     const float* scale, const float* rotation, const float* opacity, int C, int S, int A,
                                     int rest_dim, int img_h, int img_w, int true_sigmoid_grad, const float* packed_grad,
                                     const float* grad_inv_scaler, int zero_outputs, float* g_position, float* g_scale,
-                                    float* g_rotation, float* g_sh_base, float* g_sh_rest, float* g_opacity, void* stream)
+                                    float* g_rotation, float* g_sh_base, float* g_sh_rest, float* g_opacity, float* touched,
+                                    void* stream)
 {
     LGS_REQUIRE(sh_degree >= 0 && sh_degree <= 3, "project_backward: sh_degree %d not in 0..3", sh_degree);
     LGS_REQUIRE(rest_dim >= (sh_degree + 1) * (sh_degree + 1) - 1, "project_backward: sh_rest has %d rows, degree %d needs %d", rest_dim,
@@ -448,7 +450,7 @@ extern "C" int lgs_project_backward(int sh_degree, const int64_t* visible_chunk_
     }
 #define PB(D) project_backward_kernel<D><<<A, S, 0, st>>>(visible_chunk_id, visible_chunks_num, view_matrix, proj_matrix, position, scale, \
         rotation, opacity, C, S, A, rest_dim, img_h, img_w, true_sigmoid_grad, accumulate, packed_grad, grad_inv_scaler, g_position, g_scale, \
-        g_rotation, g_sh_base, g_sh_rest, g_opacity)
+        g_rotation, g_sh_base, g_sh_rest, g_opacity, touched)
     switch (sh_degree) { case 0: PB(0); break; case 1: PB(1); break; case 2: PB(2); break; default: PB(3); }
 #undef PB
     LGS_CHECK_LAUNCH("project_backward_kernel");

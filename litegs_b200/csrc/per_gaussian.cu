@@ -28,54 +28,74 @@ extern "C" int lgs_abi_version(void) { return 1; }
 
 // ------------------------------------------------------------------------------------------------
 // frustum culling of chunk AABBs + ordered stream compaction.   replaces GR/compact.cu:419-551
-// One CTA of 1024 threads walks the M chunks in slabs; a block-wide ballot scan gives every visible
-// chunk its rank, so the compacted ids come out in ascending order (deterministic; the reference's
-// atomics give an arbitrary order).  M is ~8k at 1M Gaussians: this is a microsecond-scale kernel.
+// One CTA of 1024 threads; a block-wide ballot scan gives every visible chunk its rank, so the compacted ids come
+// out in ascending order (deterministic; the reference's atomics give an arbitrary order).  M is ~8k at 1M
+// Gaussians, i.e. 8 slabs of 1024 chunks: the kernel is pure latency, so the 8 slabs' AABB loads are issued together
+// (one round trip instead of eight) and the 8 per-slab warp-count scans run in parallel on 8 warps (two barriers per
+// 8192 chunks instead of 24).
 // ------------------------------------------------------------------------------------------------
+constexpr int CULL_U = 8;
 __global__ void __launch_bounds__(1024) frustum_cull_kernel(
     const float* __restrict__ origin, const float* __restrict__ ext, const float* __restrict__ planes,
     int M, int V, uint8_t* __restrict__ visibility, int* __restrict__ visible_num, int64_t* __restrict__ ids)
 {
-    __shared__ int warp_counts[32];
-    __shared__ int slab_base;
+    __shared__ int warp_counts[CULL_U][32];     // visible chunks per warp, per slab; then their exclusive prefix
+    __shared__ int slab_total[CULL_U];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) slab_base = 0;
-    __syncthreads();
-    for (int base = 0; base < M; base += blockDim.x) {
-        int m = base + threadIdx.x;
-        bool vis = false;
-        if (m < M) {
-            float ox = origin[m], oy = origin[M + m], oz = origin[2 * M + m];
-            float ex = ext[m], ey = ext[M + m], ez = ext[2 * M + m];
-            for (int n = 0; n < V; n++) {
-                bool in = true;
+    int running = 0;                            // chunks emitted by earlier groups (same value in every thread)
+    for (int base0 = 0; base0 < M; base0 += 1024 * CULL_U) {
+        float o[CULL_U][3], e[CULL_U][3];
 #pragma unroll
-                for (int p = 0; p < 6; p++) {
-                    const float* pl = planes + (n * 6 + p) * 4;
-                    // plain IEEE expression order (no FMA contraction) so the decision is reproducible
-                    float d0 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(pl[0], ox), __fmul_rn(pl[1], oy)), __fmul_rn(pl[2], oz)), pl[3]);
-                    float de = __fadd_rn(__fadd_rn(__fmul_rn(fabsf(pl[0]), ex), __fmul_rn(fabsf(pl[1]), ey)), __fmul_rn(fabsf(pl[2]), ez));
-                    in &= (__fadd_rn(d0, de) >= 0.0f);
+        for (int u = 0; u < CULL_U; u++) {
+            const int m = base0 + u * 1024 + threadIdx.x;
+            const bool in = m < M;
+#pragma unroll
+            for (int k = 0; k < 3; k++) { o[u][k] = in ? origin[k * M + m] : 0.0f; e[u][k] = in ? ext[k * M + m] : 0.0f; }
+        }
+        unsigned ballots[CULL_U];
+#pragma unroll
+        for (int u = 0; u < CULL_U; u++) {
+            const int m = base0 + u * 1024 + threadIdx.x;
+            bool vis = false;
+            if (m < M) {
+                for (int n = 0; n < V; n++) {
+                    bool in = true;
+#pragma unroll
+                    for (int p = 0; p < 6; p++) {
+                        const float* pl = planes + (n * 6 + p) * 4;
+                        // plain IEEE expression order (no FMA contraction) so the decision is reproducible
+                        float d0 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(pl[0], o[u][0]), __fmul_rn(pl[1], o[u][1])), __fmul_rn(pl[2], o[u][2])), pl[3]);
+                        float de = __fadd_rn(__fadd_rn(__fmul_rn(fabsf(pl[0]), e[u][0]), __fmul_rn(fabsf(pl[1]), e[u][1])), __fmul_rn(fabsf(pl[2]), e[u][2]));
+                        in &= (__fadd_rn(d0, de) >= 0.0f);
+                    }
+                    vis |= in;
                 }
-                vis |= in;
+                visibility[m] = vis ? 1 : 0;
             }
-            visibility[m] = vis ? 1 : 0;
-        }
-        unsigned ballot = __ballot_sync(0xffffffffu, vis);
-        if (lane == 0) warp_counts[warp] = __popc(ballot);
-        __syncthreads();
-        int before = slab_base;
-        for (int w = 0; w < warp; w++) before += warp_counts[w];
-        if (vis) ids[before + __popc(ballot & ((1u << lane) - 1u))] = m;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int tot = 0;
-            for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot += warp_counts[w];
-            slab_base += tot;
+            ballots[u] = __ballot_sync(0xffffffffu, vis);
+            if (lane == 0) warp_counts[u][warp] = __popc(ballots[u]);
         }
         __syncthreads();
+        if (warp < CULL_U) {                    // warp u scans slab u's 32 warp counts
+            const int c = warp_counts[warp][lane];
+            int inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+            warp_counts[warp][lane] = inc - c;
+            if (lane == 31) slab_total[warp] = inc;
+        }
+        __syncthreads();
+        int before = running;
+#pragma unroll
+        for (int u = 0; u < CULL_U; u++) {
+            const int m = base0 + u * 1024 + threadIdx.x;
+            if ((ballots[u] >> lane) & 1u) ids[before + warp_counts[u][warp] + __popc(ballots[u] & ((1u << lane) - 1u))] = m;
+            before += slab_total[u];
+        }
+        running = before;
+        __syncthreads();                        // the shared arrays are rewritten by the next group
     }
-    if (threadIdx.x == 0) visible_num[0] = slab_base;
+    if (threadIdx.x == 0) visible_num[0] = running;
 }
 
 extern "C" int lgs_frustum_culling_aabb(const float* aabb_origin, const float* aabb_ext, const float* frustumplane,

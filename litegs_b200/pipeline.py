@@ -216,10 +216,8 @@ def render_view_backward(params: dict, state: ViewState, d_img: torch.Tensor, d_
                 _lib.call("lgs_project_backward", state.sh_degree, _ptr(state.chunk_ids), ctypes.c_void_p(state.counters.data_ptr()),
                           _ptr(state.view), _ptr(state.proj), _ptr(xyz), _ptr(params["scale"]), _ptr(params["rot"]),
                           _ptr(params["opacity"]), C, S, A, R, H, W, int(CONFIG["true_sigmoid_grad"]), _ptr(pg), None, 2,
-                          _ptr(d["xyz"]), _ptr(d["scale"]), _ptr(d["rot"]), _ptr(d["sh_0"]), _ptr(d["sh_rest"]), _ptr(d["opacity"]), st)
-                if d.get("_touched") is not None:       # chunk marks for the fused optimizer step (GradAccumulator.touched)
-                    _lib.call("lgs_mark_visible_chunks", _ptr(state.chunk_ids), ctypes.c_void_p(state.counters.data_ptr()), A,
-                              _ptr(d["_touched"]), st)
+                          _ptr(d["xyz"]), _ptr(d["scale"]), _ptr(d["rot"]), _ptr(d["sh_0"]), _ptr(d["sh_rest"]), _ptr(d["opacity"]),
+                          _ptr(d.get("_touched")), st)   # "_touched": chunk marks for the fused optimizer step
             return None, pg
         g_pos = torch.empty((3, A, S), dtype=_F32, device=dev)
         g_sc = torch.empty((3, A, S), dtype=_F32, device=dev)
@@ -232,5 +230,5 @@ def render_view_backward(params: dict, state: ViewState, d_img: torch.Tensor, d_
             _lib.call("lgs_project_backward", state.sh_degree, _ptr(state.chunk_ids), ctypes.c_void_p(state.counters.data_ptr()),
                       _ptr(state.view), _ptr(state.proj), _ptr(xyz), _ptr(params["scale"]), _ptr(params["rot"]), _ptr(params["opacity"]),
                       C, S, A, R, H, W, int(CONFIG["true_sigmoid_grad"]), _ptr(pg), None, 0, _ptr(g_pos), _ptr(g_sc), _ptr(g_rot),
-                      _ptr(g_s0), _ptr(g_sr), _ptr(g_op), st)
+                      _ptr(g_s0), _ptr(g_sr), _ptr(g_op), None, st)
     return [g_pos, g_sc, g_rot, g_s0, g_sr, g_op], pg

@@ -111,6 +111,7 @@ class _RenderViewFn(torch.autograd.Function):
                 view_matrix, proj_matrix, sh_degree, H, W, th, tw, sparse_grad, enable_transmitance, accumulate_into):
         params = dict(xyz=xyz, scale=scale, rot=rot, sh_0=sh_0, sh_rest=sh_rest, opacity=opacity)
         stat = bool(StatisticsHelperInst.bStart)
+        ctx.set_materialize_grads(False)       # an unused transmittance output must not cost a zero-filled gradient image
         # the kernel writes clamp(c,0,1) directly (render/__init__.py:87 does it as a separate pass) ...
         img, state, stats = pipeline.render_view_forward(params, cluster_origin, cluster_extend, frustumplane, view_matrix,
                                                          proj_matrix, sh_degree, (H, W), (th, tw), enable_statistic=stat, clamp_zero=True)
@@ -132,7 +133,8 @@ class _RenderViewFn(torch.autograd.Function):
         if g_img is None:
             g_img = torch.zeros((1, 3, *state.T.shape[-2:]), dtype=torch.float32, device=xyz.device)
         # ... and the backward kernel applies that clamp's gradient mask from the saved image
-        grads, pg = pipeline.render_view_backward(params, state, g_img, g_T if ctx.trans else None, enable_statistic=ctx.stat,
+        grads, pg = pipeline.render_view_backward(params, state, g_img, g_T if (ctx.trans and g_T is not None) else None,
+                                                  enable_statistic=ctx.stat,
                                                   accumulate_into=ctx.accumulate_into, clamped_img=img_out)
         if ctx.stat and StatisticsHelperInst.on_fragment_weight is not None:
             StatisticsHelperInst.on_fragment_weight(ctx.stats[1], ctx.stats[0])
@@ -192,7 +194,9 @@ def render_views(n_views: int, camera_fn, loss_fn, cluster_origin, cluster_exten
     like the parameters, e.g. ``GradAccumulator.grads()``).  This is the per-rank body of a data-parallel step.
 
     ``camera_fn(i)`` -> dict(view, proj, frustumplane) and ``loss_fn(i, img)`` -> scalar loss are called with view i's
-    stream current (so H2D copies issued inside them are ordered correctly).  Consecutive views alternate over
+    stream current (so H2D copies issued inside them are ordered correctly).  ``loss_fn`` may instead return
+    ``(loss, d_img)`` -- the scalar and dloss/dimg computed outside autograd, e.g. ``ssim.l1_ssim_loss_and_grad(img.detach(),
+    gt)`` -- in which case the image gradient is fed straight to the rasterizer's backward.  Consecutive views alternate over
     ``n_streams`` CUDA streams: view i+1's forward (bandwidth-bound projection / sort kernels and the one host
     read-back) overlaps view i's backward (issue-bound raster kernel).  Views only interact through the dense
     accumulate, which is ordered by an event.  Returns the list of (detached) per-view losses."""
@@ -206,7 +210,11 @@ def render_views(n_views: int, camera_fn, loss_fn, cluster_origin, cluster_exten
         loss = loss_fn(i, img)
         if wait_ev is not None:          # the previous view's accumulate (other stream) must have landed
             torch.cuda.current_stream(dev).wait_event(wait_ev)
-        loss.backward()
+        if isinstance(loss, tuple):
+            loss, d_img = loss
+            img.backward(d_img)
+        else:
+            loss.backward()
         losses.append(loss.detach())
 
     if n_streams <= 1:

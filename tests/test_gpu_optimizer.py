@@ -83,8 +83,8 @@ def test_untouched_chunks_do_not_move_and_all_chunks_mode(cuda):
 
 
 def test_render_views_marks_visible_chunks_and_training_step_runs(cuda):
-    """End to end: render_views accumulates gradients + marks, the fused step consumes them; a second identical step
-    from restored parameters reproduces the first bit for bit (deterministic)."""
+    """End to end: render_views accumulates gradients + marks, the fused step consumes them; the same step again from
+    restored parameters, with the loss gradient computed outside autograd, lands on the same parameters."""
     from litegs_b200 import render, ssim
     from litegs_b200.arguments import PipelineParams
     sc = scene.make_scene(6000, sh_degree=3, seed=2)
@@ -99,8 +99,10 @@ def test_render_views_marks_visible_chunks_and_training_step_runs(cuda):
         acc = lgs_dist.GradAccumulator(P)
         opt, sched = optimizer.get_optimizer({k: P[k].data for k in PARAM_ORDER}, spatial_lr_scale=1.0)
 
-        def loss_fn(j, img):
-            return ssim.fused_l1_ssim_loss(img, gts[j])
+        def loss_fn(j, img):         # rep 0: the reference-shaped autograd surface; rep 1: loss + image gradient outside autograd
+            if rep == 0:
+                return ssim.fused_l1_ssim_loss(img, gts[j])
+            return ssim.l1_ssim_loss_and_grad(img.detach(), gts[j], 0.2)
 
         losses = render.render_views(3, lambda j: cams[j], loss_fn, A[0], A[1], P["xyz"], P["scale"], P["rot"], P["sh_0"], P["sh_rest"],
                                      P["opacity"], 3, (H, W), pp, acc.grads(), n_streams=2)
