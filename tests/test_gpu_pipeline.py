@@ -73,11 +73,15 @@ def test_level_a_and_b_match_oracle(cuda, tile, sh_degree):
     assert np.abs(img.detach().cpu().numpy() - img2.detach().cpu().numpy()).max() < 1e-5
 
 
-def test_fused_pairs_match_oracle_lists(cuda):
+@pytest.mark.parametrize("hw,tile,n,scales", [((96, 128), (16, 16), 4000, (0.02, 0.08)),
+                                               # 32 x 32 tiles of 8 x 8 and splats hundreds of pixels wide: long tile walks, runs
+                                               # longer than the emit pass's shared-memory window
+                                               ((256, 256), (8, 8), 1500, (0.05, 0.5)),
+                                               ((120, 200), (8, 16), 3000, (0.01, 0.2))])
+def test_fused_pairs_match_oracle_lists(cuda, hw, tile, n, scales):
     """The fused pipeline's per-tile splat lists equal the oracle's (identical order) on a seeded scene."""
     from litegs_b200 import pipeline
-    hw, tile = (96, 128), (16, 16)
-    params, aabb, cam = small_scene(n=4000, hw=hw, seed=3)
+    params, aabb, cam = small_scene(n=n, hw=hw, seed=3, log_scale_range=scales)
     P, A, C = _to_torch(params, aabb, cam, cuda, grad=False)
     img, st, _ = pipeline.render_view_forward(P, A[0], A[1], C["frustumplane"], C["view"], C["proj"], 3, hw, tile)
     from tests.util import oracle_projected
