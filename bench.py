@@ -42,7 +42,7 @@ PARAM_KEYS = ("xyz", "scale", "rot", "sh_0", "sh_rest", "opacity")
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gaussians", type=int, default=1_000_000)
@@ -148,6 +148,16 @@ class StageTimer:
         for name, evs in self.rec.items():
             out[name] = (sum(a.elapsed_time(b) for a, b in evs), len(evs))
         return out
+
+
+def _max_list_len(ranges, n_pairs):
+    """Longest per-tile list: ranges[t] = first pair of tile t or -1 (empty); a list ends where the next populated tile starts."""
+    import torch
+    r = ranges.to(torch.int64).clone()
+    r[r < 0] = n_pairs + 1
+    nxt = torch.flip(torch.cummin(torch.flip(r, [0]), 0).values, [0])       # nxt[t] = first start at or after t
+    ln = (nxt[1:] - ranges[:-1].to(torch.int64))[ranges[:-1] >= 0]
+    return int(ln[ln <= n_pairs].max().item()) if ln.numel() else 0
 
 
 def load_scene(args):
@@ -413,7 +423,7 @@ def run_ours(args, rank, world, local_rank):
                  "N_visible": int((st.tile_count[: st.n_chunks_visible * S] > 0).sum().item()),
                  "tiles": gx * gy, "tile_sort_passes": math.ceil((gx * gy).bit_length() / 8),
                  "mean_contributors_per_pixel": float(st.last.float().mean().item()),
-                 "max_list_len": int((st.ranges[0, 1:] - st.ranges[0, :-1]).clamp_min(0).max().item())}
+                 "max_list_len": _max_list_len(st.ranges[0], st.n_pairs)}
 
     # ---- e2e: host inputs, H2D + D2H inside the timed region ------------------------------------------
     e2e = None
