@@ -454,7 +454,7 @@ def run_ours(args, rank, world, local_rank):
             a.zero_()
             out = run_views(e2e_camera, e2e_loss)
             if world > 1:
-                a.all_reduce()
+                a.all_reduce(async_op=(args.level == "B"))     # overlaps the next step, as in the resident-input loop
             step_no["k"] += 1
             torch.cuda.current_stream(dev).synchronize()          # the step's losses are on the host now
             if args.level == "A":
@@ -468,6 +468,8 @@ def run_ours(args, rank, world, local_rank):
         f0.record()
         for _ in range(n_e2e):
             e2e_step()
+        for a in accs:
+            a.wait()                   # the last steps' all-reduces end inside the timed region
         f1.record()
         barrier()
         t2 = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
