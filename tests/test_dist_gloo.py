@@ -92,3 +92,10 @@ def test_two_rank_gradient_allreduce_matches_single_process():
     # identical on both ranks (replicated optimiser steps stay in lock-step)
     for k in PARAM_ORDER:
         assert np.array_equal(results[0][k], results[1][k])
+    # the chunk marks ride in the same all-reduce: non-zero exactly at the chunks visible in some view on some rank
+    seen = np.zeros(6, bool)
+    for v in range(n_views):
+        _, ids, n = _view_grads(v)
+        seen[ids[: int(n)].numpy()] = True
+    for r in range(2):
+        assert np.array_equal(results[r]["_touched"] > 0, seen), r
