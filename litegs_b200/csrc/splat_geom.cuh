@@ -10,7 +10,7 @@
 #pragma once
 
 struct SplatGeom {
-    float A, B, C, disc, t, px, py;
+    float A, B, C, inv_A, inv_C, disc, t, px, py;
     float bbox_min[2], bbox_max[2], argmin[2], argmax[2];  // [0]=x-ish, [1]=y-ish exactly as the reference's float2
     int rect_min[2], rect_max[2];
     bool visible;
@@ -27,17 +27,21 @@ __device__ __forceinline__ float lgs_div_tile(float x)
     return __fdiv_rn(x, (float)T);
 }
 
-__device__ __forceinline__ void lgs_ellipse_isect(float A, float B, float C, float disc, float t, float px, float py,
-                                                  bool isY, float coord, float& lo, float& hi)
+// The two quotients by A (or C) are products with the splat's once-rounded reciprocal inv_A = 1/A (inv_C = 1/C): what the
+// reference's own fast-math build does (x/c -> x * rcp(c)), one IEEE division per splat and axis instead of two per tile
+// row, and the same operation sequence as the oracle (oracle_core.h: ellipse_isect).
+__device__ __forceinline__ void lgs_ellipse_isect(float A, float B, float C, float inv_A, float inv_C, float disc, float t, float px,
+                                                  float py, bool isY, float coord, float& lo, float& hi)
 {
     float p_u = isY ? py : px;
     float p_v = isY ? px : py;
     float coeff = isY ? A : C;
+    float inv = isY ? inv_A : inv_C;
     float h = __fsub_rn(coord, p_u);
     float sq = __fsqrt_rn(__fadd_rn(__fmul_rn(__fmul_rn(disc, h), h), __fmul_rn(t, coeff)));
     float nbh = __fmul_rn(-B, h);
-    lo = __fadd_rn(__fdiv_rn(__fsub_rn(nbh, sq), coeff), p_v);
-    hi = __fadd_rn(__fdiv_rn(__fadd_rn(nbh, sq), coeff), p_v);
+    lo = __fadd_rn(__fmul_rn(__fsub_rn(nbh, sq), inv), p_v);
+    hi = __fadd_rn(__fmul_rn(__fadd_rn(nbh, sq), inv), p_v);
 }
 
 // check_visibility=false reproduces the emit kernel, which trusts the count it was given
@@ -59,6 +63,7 @@ __device__ __forceinline__ void lgs_splat_setup(float ndcx, float ndcy, float vi
     if (!vis) return;
     float t = (float)(2.0 * log((double)__fmul_rn(o, 255.0f)));
     g.t = t;
+    g.inv_A = __fdiv_rn(1.0f, A); g.inv_C = __fdiv_rn(1.0f, C);
     float bbt = __fmul_rn(__fmul_rn(B, B), t);
     float xt = __fsqrt_rn(__fdiv_rn(-bbt, __fmul_rn(g.disc, A)));
     xt = (B < 0.0f) ? xt : -xt;
@@ -67,10 +72,10 @@ __device__ __forceinline__ void lgs_splat_setup(float ndcx, float ndcy, float vi
     g.argmin[0] = __fsub_rn(g.py, yt); g.argmin[1] = __fsub_rn(g.px, xt);
     g.argmax[0] = __fadd_rn(g.py, yt); g.argmax[1] = __fadd_rn(g.px, xt);
     float lo, hi;
-    lgs_ellipse_isect(A, B, C, g.disc, t, g.px, g.py, true, g.argmin[0], lo, hi);  g.bbox_min[0] = lo;
-    lgs_ellipse_isect(A, B, C, g.disc, t, g.px, g.py, false, g.argmin[1], lo, hi); g.bbox_min[1] = lo;
-    lgs_ellipse_isect(A, B, C, g.disc, t, g.px, g.py, true, g.argmax[0], lo, hi);  g.bbox_max[0] = hi;
-    lgs_ellipse_isect(A, B, C, g.disc, t, g.px, g.py, false, g.argmax[1], lo, hi); g.bbox_max[1] = hi;
+    lgs_ellipse_isect(A, B, C, g.inv_A, g.inv_C, g.disc, t, g.px, g.py, true, g.argmin[0], lo, hi);  g.bbox_min[0] = lo;
+    lgs_ellipse_isect(A, B, C, g.inv_A, g.inv_C, g.disc, t, g.px, g.py, false, g.argmin[1], lo, hi); g.bbox_min[1] = lo;
+    lgs_ellipse_isect(A, B, C, g.inv_A, g.inv_C, g.disc, t, g.px, g.py, true, g.argmax[0], lo, hi);  g.bbox_max[0] = hi;
+    lgs_ellipse_isect(A, B, C, g.inv_A, g.inv_C, g.disc, t, g.px, g.py, false, g.argmax[1], lo, hi); g.bbox_max[1] = hi;
     g.rect_min[0] = max(0, min(gx, lgs_f2i_rz(lgs_div_tile<TW>(g.bbox_min[0]))));
     g.rect_min[1] = max(0, min(gy, lgs_f2i_rz(lgs_div_tile<TH>(g.bbox_min[1]))));
     g.rect_max[0] = max(0, min(gx, lgs_f2i_rz(lgs_div_tile<TW>(__fsub_rn(__fadd_rn(g.bbox_max[0], (float)TW), 1.0f)))));
@@ -98,11 +103,11 @@ __device__ __forceinline__ int lgs_process_tiles(const SplatGeom& g, int gx, int
     float imax_lo = bmax1, imax_hi = bmin1;
     float imin_lo, imin_hi;
     float min_line = __fmul_rn((float)rmin0, BU), max_line;
-    if (bmin0 <= min_line) lgs_ellipse_isect(g.A, g.B, g.C, g.disc, g.t, g.px, g.py, isY, min_line, imin_lo, imin_hi);
+    if (bmin0 <= min_line) lgs_ellipse_isect(g.A, g.B, g.C, g.inv_A, g.inv_C, g.disc, g.t, g.px, g.py, isY, min_line, imin_lo, imin_hi);
     else { imin_lo = imax_lo; imin_hi = imax_hi; }
     for (int u = rmin0; u < rmax0; ++u) {
         max_line = __fadd_rn(min_line, BU);
-        if (max_line <= bmax0) lgs_ellipse_isect(g.A, g.B, g.C, g.disc, g.t, g.px, g.py, isY, max_line, imax_lo, imax_hi);
+        if (max_line <= bmax0) lgs_ellipse_isect(g.A, g.B, g.C, g.inv_A, g.inv_C, g.disc, g.t, g.px, g.py, isY, max_line, imax_lo, imax_hi);
         float emin, emax;
         if (min_line <= amin1 && amin1 < max_line) emin = bmin1; else emin = fminf(imin_lo, imax_lo);
         if (min_line <= amax1 && amax1 < max_line) emax = bmax1; else emax = fmaxf(imin_hi, imax_hi);

@@ -476,21 +476,25 @@ void SUF(orc_inv2x2_backward)(const REAL* inv, const REAL* g_inv, int V, int N, 
 
 /* ---- binning -------------------------------------------------------------------------- */
 
-/* GR/speedy_splat.cuh:16-31 */
-static inline void SUF(ellipse_isect)(REAL A, REAL B, REAL Cc, REAL disc, REAL t, REAL px, REAL py,
+/* GR/speedy_splat.cuh:16-31.  The two quotients by A (or C) are taken as products with the once-rounded reciprocal
+ * inv_A = 1/A (inv_C = 1/C) of the splat: the reference's own build does the same (--use_fast_math turns x/c into
+ * x * rcp(c), GR/setup.py:35), and one division per splat and axis replaces two per tile row.  The CUDA kernels
+ * (csrc/splat_geom.cuh) use the identical operation sequence, so tile decisions stay bit-identical CPU <-> GPU. */
+static inline void SUF(ellipse_isect)(REAL A, REAL B, REAL Cc, REAL inv_A, REAL inv_C, REAL disc, REAL t, REAL px, REAL py,
                                       int isY, REAL coord, REAL* lo, REAL* hi)
 {
     REAL p_u = isY ? py : px;
     REAL p_v = isY ? px : py;
     REAL coeff = isY ? A : Cc;
+    REAL inv = isY ? inv_A : inv_C;
     REAL h = coord - p_u;
     REAL sq = SQRT(disc * h * h + t * coeff);
-    *lo = (-B * h - sq) / coeff + p_v;
-    *hi = (-B * h + sq) / coeff + p_v;
+    *lo = (-B * h - sq) * inv + p_v;
+    *hi = (-B * h + sq) * inv + p_v;
 }
 
 typedef struct {
-    REAL A, B, C, disc, t, px, py;
+    REAL A, B, C, inv_A, inv_C, disc, t, px, py;
     REAL bbox_min[2], bbox_max[2], argmin[2], argmax[2];
     int rect_min[2], rect_max[2];
     int visible;
@@ -513,6 +517,7 @@ static inline void SUF(splat_setup)(REAL ndcx, REAL ndcy, REAL viewz, REAL A, RE
     if (!vis) return;
     REAL t = (REAL)(2.0 * log((double)(o * (REAL)255.0)));
     g->t = t;
+    g->inv_A = (REAL)1 / A; g->inv_C = (REAL)1 / Cc;
     REAL xt = SQRT(-(B * B * t) / (g->disc * A));
     xt = (B < 0) ? xt : -xt;
     REAL yt = SQRT(-(B * B * t) / (g->disc * Cc));
@@ -520,10 +525,10 @@ static inline void SUF(splat_setup)(REAL ndcx, REAL ndcy, REAL viewz, REAL A, RE
     g->argmin[0] = g->py - yt; g->argmin[1] = g->px - xt;
     g->argmax[0] = g->py + yt; g->argmax[1] = g->px + xt;
     REAL lo, hi;
-    SUF(ellipse_isect)(A, B, Cc, g->disc, t, g->px, g->py, 1, g->argmin[0], &lo, &hi); g->bbox_min[0] = lo;
-    SUF(ellipse_isect)(A, B, Cc, g->disc, t, g->px, g->py, 0, g->argmin[1], &lo, &hi); g->bbox_min[1] = lo;
-    SUF(ellipse_isect)(A, B, Cc, g->disc, t, g->px, g->py, 1, g->argmax[0], &lo, &hi); g->bbox_max[0] = hi;
-    SUF(ellipse_isect)(A, B, Cc, g->disc, t, g->px, g->py, 0, g->argmax[1], &lo, &hi); g->bbox_max[1] = hi;
+    SUF(ellipse_isect)(A, B, Cc, g->inv_A, g->inv_C, g->disc, t, g->px, g->py, 1, g->argmin[0], &lo, &hi); g->bbox_min[0] = lo;
+    SUF(ellipse_isect)(A, B, Cc, g->inv_A, g->inv_C, g->disc, t, g->px, g->py, 0, g->argmin[1], &lo, &hi); g->bbox_min[1] = lo;
+    SUF(ellipse_isect)(A, B, Cc, g->inv_A, g->inv_C, g->disc, t, g->px, g->py, 1, g->argmax[0], &lo, &hi); g->bbox_max[0] = hi;
+    SUF(ellipse_isect)(A, B, Cc, g->inv_A, g->inv_C, g->disc, t, g->px, g->py, 0, g->argmax[1], &lo, &hi); g->bbox_max[1] = hi;
     g->rect_min[0] = SUF(imax)(0, SUF(imin)(gx, SUF(f2i_rz)(g->bbox_min[0] / TW)));
     g->rect_min[1] = SUF(imax)(0, SUF(imin)(gy, SUF(f2i_rz)(g->bbox_min[1] / TH)));
     g->rect_max[0] = SUF(imax)(0, SUF(imin)(gx, SUF(f2i_rz)((g->bbox_max[0] + TW - 1) / TW)));
@@ -555,12 +560,12 @@ static inline int SUF(process_tiles)(const SUF(splat_geom)* g, int TH, int TW, i
     REAL imin_lo, imin_hi;
     REAL min_line = rmin[0] * BU, max_line;
     if (bmin[0] <= min_line)
-        SUF(ellipse_isect)(g->A, g->B, g->C, g->disc, g->t, g->px, g->py, isY, rmin[0] * BU, &imin_lo, &imin_hi);
+        SUF(ellipse_isect)(g->A, g->B, g->C, g->inv_A, g->inv_C, g->disc, g->t, g->px, g->py, isY, rmin[0] * BU, &imin_lo, &imin_hi);
     else { imin_lo = imax_lo; imin_hi = imax_hi; }
     for (int u = rmin[0]; u < rmax[0]; ++u) {
         max_line = min_line + BU;
         if (max_line <= bmax[0])
-            SUF(ellipse_isect)(g->A, g->B, g->C, g->disc, g->t, g->px, g->py, isY, max_line, &imax_lo, &imax_hi);
+            SUF(ellipse_isect)(g->A, g->B, g->C, g->inv_A, g->inv_C, g->disc, g->t, g->px, g->py, isY, max_line, &imax_lo, &imax_hi);
         REAL emin, emax;
         if (min_line <= amin[1] && amin[1] < max_line) emin = bmin[1];
         else emin = FMIN(imin_lo, imax_lo);
