@@ -42,7 +42,6 @@ def test_fused_step_matches_sparse_adam_on_touched_chunks(cuda):
             p3, m3, v3 = ref[k].reshape(R, C, S), ref_m[k].reshape(R, C, S), ref_v[k].reshape(R, C, S)
             gc = grads[k].numpy().reshape(R, C, S)[:, touched.numpy(), :]
             oracle.adamUpdate(p3, np.ascontiguousarray(gc), m3, v3, touched.numpy(), None, lr[k], 0.9, 0.999, 1e-15)
-        assert float(acc.flat.abs().max()) == 0.0 or True
         # consumed rows and marks are cleared; rows of untouched chunks keep the (never consumed) gradient
         assert float(acc.touched.abs().max()) == 0.0
         mask = torch.zeros(C, dtype=torch.bool)

@@ -195,3 +195,21 @@ def test_against_reference_kernels_live(cuda):
     for name, u, v in (("map", m, rm), ("dm_dmu1", d0, r0), ("dm_dsigma1_sq", d1, r1), ("dm_dsigma12", d2, r2), ("grad", gg, rg)):
         err = float((u - v).abs().max() / max(1.0, float(v.abs().max())))
         assert err < TOL, (name, err)
+
+
+def test_reference_own_consistency_check(cuda):
+    """The reference's own test (fused_ssim/tests/test_fused_l1_ssim_loss.py:10-45) on our implementation: the fused
+    L1+SSIM loss equals (1 - w) * L1 + w * (1 - fused_ssim) assembled from the separate SSIM op, value and gradient
+    (torch.isclose defaults, as there), on a 1080p random pair."""
+    w = 0.2
+    g = torch.Generator(device="cpu").manual_seed(0)
+    gt = torch.rand((3, 1080, 1920), generator=g).to(cuda)
+    im = torch.rand((3, 1080, 1920), generator=g).to(cuda)
+    a = im.clone().requires_grad_(True)
+    before = (1.0 - w) * torch.abs(a - gt).mean() + w * (1.0 - ssim.fused_ssim(a.unsqueeze(0), gt.unsqueeze(0)))
+    before.backward()
+    b = im.clone().requires_grad_(True)
+    after = ssim.fused_l1_ssim_loss(b.unsqueeze(0), gt.unsqueeze(0), w)
+    after.backward()
+    assert torch.isclose(before, after)
+    assert torch.isclose(a.grad, b.grad).all()
