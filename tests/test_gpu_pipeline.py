@@ -44,10 +44,11 @@ def _check(img, grads, nvis, ref, frag, what):
         assert e < 2e-4, (what, k, e)
 
 
-@pytest.mark.parametrize("tile,sh_degree", [((16, 16), 3), ((8, 16), 2), ((8, 8), 0)])
-def test_level_a_and_b_match_oracle(cuda, tile, sh_degree):
-    hw = (96, 128)
-    params, aabb, cam, w, frag, ref = _case(4000, hw, tile, sh_degree, seed=11)
+@pytest.mark.parametrize("tile,sh_degree,n,hw", [((16, 16), 3, 4000, (96, 128)), ((8, 16), 2, 4000, (96, 128)), ((8, 8), 0, 4000, (96, 128)),
+                                                 # BASELINE.json configs[0] ("C1"): 10k Gaussians, 256 x 256, one view
+                                                 ((8, 16), 3, 10000, (256, 256)), ((12, 16), 3, 10000, (256, 256))])
+def test_level_a_and_b_match_oracle(cuda, tile, sh_degree, n, hw):
+    params, aabb, cam, w, frag, ref = _case(n, hw, tile, sh_degree, seed=11)
     nvis = int(ref["visible_chunk_id"].shape[0])
     pp = PipelineParams(tile_size=tile)
     wt = torch.from_numpy(w).to(cuda)
