@@ -13,9 +13,11 @@
 //    records are then read back as conflict-free broadcast LDS.128;
 //  * fp32 throughout (ex2.approx.ftz for the Gaussian): the 1e-4 parity gate of BASELINE.json rules out
 //    the reference's packed-half blend;
-//  * backward: per-(tile, splat) gradients are reduced over the tile's pixels entirely inside the warp
-//    (per-lane polynomial moments in dy, then a 9-shuffle transposing butterfly for 8 values) and
-//    leave the SM exactly once, as one predicated RED.ADD.F32 touching a single 48-byte record.
+//  * backward: per-(tile, splat) gradients are reduced over the tile's pixels entirely inside the warp --
+//    per-lane polynomial moments in dy, then either a transposed sum through a per-warp shared-memory
+//    matrix (default: 9 conflict-free STS per splat, every 3 splats 27 lanes each add up one row with
+//    8 LDS.128) or a 9-shuffle transposing butterfly -- and leave the SM exactly once, as one
+//    RED.ADD.F32 per value touching a single 48-byte record.
 #include "common.cuh"
 
 #define FULL_MASK 0xffffffffu
