@@ -50,11 +50,11 @@ def train(n_gaussians=50_000, hw=(270, 480), n_views=16, iters=100, seed=0, devi
     history = []
     t0 = time.perf_counter()
     for it in range(iters):
-        losses = render.render_views(len(mine), lambda i: cams[mine[i]],
-                                     lambda i, img: ssim.l1_ssim_loss_and_grad(img.detach().contiguous(), gts[mine[i]], 0.2,
-                                                                               upstream=1.0 / (len(mine) * world)),
+        losses = render.render_views(len(mine), lambda i: cams[mine[i]], None,
                                      A[0], A[1], P["xyz"], P["scale"], P["rot"], P["sh_0"], P["sh_rest"], P["opacity"], 3, (H, W), pp,
-                                     acc.grads())
+                                     acc.grads(),
+                                     loss_and_grad_fn=lambda i, img: ssim.l1_ssim_loss_and_grad(img.contiguous(), gts[mine[i]], 0.2,
+                                                                                              upstream=1.0 / (len(mine) * world)))
         acc.all_reduce()
         opt.step(acc)
         sched.step()

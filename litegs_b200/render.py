@@ -8,6 +8,7 @@ Level B is what ``bench.py`` measures.
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -178,6 +179,9 @@ def render_view(cluster_origin, cluster_extend, frustumplane, view_matrix, proj_
 # ---------------------------------------------------------------------------------------------------
 
 _side_streams: dict = {}
+# render_views drives the pipeline's forward/backward directly and uses autograd only for the caller's loss (default);
+# LGS_VIEWS_AUTOGRAD=1 routes every view through the render_view autograd Function instead (A/B switch)
+_DIRECT_VIEWS = os.environ.get("LGS_VIEWS_AUTOGRAD", "0") != "1"
 
 
 def _streams(dev, n):
@@ -189,7 +193,7 @@ def _streams(dev, n):
 
 def render_views(n_views: int, camera_fn, loss_fn, cluster_origin, cluster_extend,
                  xyz, scale, rot, sh_0, sh_rest, opacity, actived_sh_degree: int, output_shape, pp,
-                 accumulate_into: dict, n_streams: int = 3):
+                 accumulate_into: dict, n_streams: int = 3, loss_and_grad_fn=None):
     """Forward + backward of a batch of views with the gradients summed into ``accumulate_into`` (dense tensors shaped
     like the parameters, e.g. ``GradAccumulator.grads()``).  This is the per-rank body of a data-parallel step.
 
@@ -199,11 +203,45 @@ def render_views(n_views: int, camera_fn, loss_fn, cluster_origin, cluster_exten
     gt)`` -- in which case the image gradient is fed straight to the rasterizer's backward.  Consecutive views alternate over
     ``n_streams`` CUDA streams: view i+1's forward (bandwidth-bound projection / sort kernels and the one host
     read-back) overlaps view i's backward (issue-bound raster kernel).  Views only interact through the dense
-    accumulate, which is ordered by an event.  Returns the list of (detached) per-view losses."""
+    accumulate, which is ordered by an event.  Returns the list of (detached) per-view losses.
+
+    ``loss_and_grad_fn(i, img) -> (loss, d_img)`` (with ``loss_fn=None``) skips autograd altogether: the pipeline's forward
+    and backward are called directly (no autograd Function, no engine hop: ~0.1 ms less host time per view), the image
+    handed to the function is the kernel's clamp(0,1) output and its gradient goes straight to the raster backward."""
     dev = xyz.device
     losses = []
+    H, W = int(output_shape[0]), int(output_shape[1])
+    th, tw = int(pp.tile_size[0]), int(pp.tile_size[1])
+    direct = loss_and_grad_fn is not None or _DIRECT_VIEWS
+    if direct:
+        params = dict(xyz=xyz.detach(), scale=scale.detach(), rot=rot.detach(), sh_0=sh_0.detach(), sh_rest=sh_rest.detach(),
+                      opacity=opacity.detach())
+        stat = bool(StatisticsHelperInst.bStart)
 
-    def one(i, wait_ev):
+    def one_direct(i, wait_ev):
+        cam = camera_fn(i)
+        img_p, state, stats = pipeline.render_view_forward(params, cluster_origin, cluster_extend, cam["frustumplane"], cam["view"],
+                                                           cam["proj"], int(actived_sh_degree), (H, W), (th, tw), enable_statistic=stat,
+                                                           clamp_zero=True)
+        if loss_and_grad_fn is not None:
+            loss, d_img = loss_and_grad_fn(i, img_p[..., :H, :W])
+        else:                          # autograd only through the user's loss, never through the render kernels
+            leaf = img_p[..., :H, :W].detach().requires_grad_(True)
+            loss = loss_fn(i, leaf)
+            if isinstance(loss, tuple):
+                loss, d_img = loss
+            else:
+                (d_img,) = torch.autograd.grad(loss, leaf)
+        if d_img.shape[-2:] != img_p.shape[-2:]:                        # image padded to whole tiles: pad the gradient with zeros
+            d_img = torch.nn.functional.pad(d_img, (0, img_p.shape[-1] - W, 0, img_p.shape[-2] - H))
+        if wait_ev is not None:
+            torch.cuda.current_stream(dev).wait_event(wait_ev)
+        pipeline.render_view_backward(params, state, d_img, None, enable_statistic=stat, accumulate_into=accumulate_into, clamped_img=img_p)
+        if stat and StatisticsHelperInst.on_fragment_weight is not None:
+            StatisticsHelperInst.on_fragment_weight(stats[1], stats[0])
+        losses.append(loss.detach())
+
+    def one_autograd(i, wait_ev):
         cam = camera_fn(i)
         img = render_view(cluster_origin, cluster_extend, cam["frustumplane"], cam["view"], cam["proj"], xyz, scale, rot, sh_0, sh_rest,
                           opacity, actived_sh_degree, output_shape, pp, accumulate_into=accumulate_into)[0]
@@ -217,6 +255,7 @@ def render_views(n_views: int, camera_fn, loss_fn, cluster_origin, cluster_exten
             loss.backward()
         losses.append(loss.detach())
 
+    one = one_direct if direct else one_autograd
     if n_streams <= 1:
         for i in range(n_views):
             one(i, None)

@@ -93,7 +93,7 @@ def test_render_views_marks_visible_chunks_and_training_step_runs(cuda):
     pp = PipelineParams(tile_size=(8, 16), sparse_grad=True)
     gts = [torch.rand((1, 3, H, W), generator=torch.Generator().manual_seed(j)).to(cuda) for j in range(3)]
     outs = []
-    for rep in range(2):
+    for rep in range(3):
         P = {k: torch.from_numpy(sc[k]).to(cuda).requires_grad_(True) for k in PARAM_ORDER}
         acc = lgs_dist.GradAccumulator(P)
         opt, sched = optimizer.get_optimizer({k: P[k].data for k in PARAM_ORDER}, spatial_lr_scale=1.0)
@@ -103,8 +103,13 @@ def test_render_views_marks_visible_chunks_and_training_step_runs(cuda):
                 return ssim.fused_l1_ssim_loss(img, gts[j])
             return ssim.l1_ssim_loss_and_grad(img.detach(), gts[j], 0.2)
 
-        losses = render.render_views(3, lambda j: cams[j], loss_fn, A[0], A[1], P["xyz"], P["scale"], P["rot"], P["sh_0"], P["sh_rest"],
-                                     P["opacity"], 3, (H, W), pp, acc.grads(), n_streams=2)
+        if rep < 2:
+            losses = render.render_views(3, lambda j: cams[j], loss_fn, A[0], A[1], P["xyz"], P["scale"], P["rot"], P["sh_0"], P["sh_rest"],
+                                         P["opacity"], 3, (H, W), pp, acc.grads(), n_streams=2)
+        else:                        # rep 2: no autograd at all (pipeline forward/backward called directly)
+            losses = render.render_views(3, lambda j: cams[j], None, A[0], A[1], P["xyz"], P["scale"], P["rot"], P["sh_0"], P["sh_rest"],
+                                         P["opacity"], 3, (H, W), pp, acc.grads(), n_streams=2,
+                                         loss_and_grad_fn=lambda j, img: ssim.l1_ssim_loss_and_grad(img.contiguous(), gts[j], 0.2))
         n_touched = int((acc.touched > 0).sum())
         assert 0 < n_touched <= acc.touched.numel()
         gsum = float(acc.buf.abs().sum())
@@ -115,7 +120,7 @@ def test_render_views_marks_visible_chunks_and_training_step_runs(cuda):
         outs.append({k: P[k].detach().clone() for k in PARAM_ORDER})
         assert all(torch.isfinite(outs[-1][k]).all() for k in PARAM_ORDER)
         assert any(not torch.equal(outs[-1][k].cpu(), torch.from_numpy(sc[k])) for k in PARAM_ORDER)
-    assert all(torch.allclose(outs[0][k], outs[1][k], rtol=1e-4, atol=1e-6) for k in PARAM_ORDER)
+    assert all(torch.allclose(outs[0][k], outs[r][k], rtol=1e-4, atol=1e-6) for k in PARAM_ORDER for r in (1, 2))
 
 
 def test_synthetic_training_loop_converges(cuda):
