@@ -30,11 +30,34 @@ CONFIG = {
 
 
 def _ptr(t: Optional[torch.Tensor]):
-    return None if t is None else ctypes.c_void_p(t.data_ptr())
+    """Raw device address for a c_void_p argument (ctypes converts the int; None is NULL)."""
+    return None if t is None else t.data_ptr()
 
 
-def _stream(dev) -> ctypes.c_void_p:
-    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+class _OnDevice:
+    """`with _on(dev):` -- torch.cuda.device(dev) only when dev is not already current (the context manager costs ~10 us,
+    and the common case is one process per GPU)."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, dev):
+        self.ctx = None if torch.cuda.current_device() == (dev.index if dev.index is not None else torch.cuda.current_device()) \
+            else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            return self.ctx.__exit__(*a)
+        return False
+
+
+_on = _OnDevice
 
 
 def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:

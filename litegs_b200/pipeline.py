@@ -19,7 +19,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from .fused import CONFIG, _ptr, _stream
+from .fused import CONFIG, _on, _ptr, _stream
 
 _F32, _I32, _I64, _U8 = torch.float32, torch.int32, torch.int64, torch.uint8
 
@@ -94,7 +94,7 @@ def render_view_forward(params: dict, cluster_origin: torch.Tensor, cluster_exte
     ntile = gx * gy
     Hp, Wp = gy * th, gx * tw
     M = C
-    with torch.cuda.device(dev):
+    with _on(dev):
         st = _stream(dev)
         counters = torch.empty(4, dtype=_I32, device=dev)
         vis = torch.empty(M, dtype=_U8, device=dev)
@@ -198,7 +198,7 @@ def render_view_backward(params: dict, state: ViewState, d_img: torch.Tensor, d_
     d_img = d_img if d_img.is_contiguous() else d_img.contiguous()
     if d_trans is not None:
         d_trans = d_trans if d_trans.is_contiguous() else d_trans.contiguous()
-    with torch.cuda.device(dev):
+    with _on(dev):
         st = _stream(dev)
         pg = torch.empty((1, Nmax, 12), dtype=_F32, device=dev)
         n_sel = 0 if specific_tiles is None else specific_tiles.shape[1]

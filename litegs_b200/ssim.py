@@ -20,7 +20,7 @@ import ctypes
 import torch
 
 from . import _lib
-from .fused import _ptr, _stream
+from .fused import _on, _ptr, _stream
 
 allowed_padding = ["same", "valid"]
 
@@ -40,7 +40,7 @@ def _forward(l1_mode: int, ssim_weight: float, C1: float, C2: float, img1, img2,
     a, b = _check(img1, img2)
     B, CH, H, W = a.shape
     dev = a.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         out = torch.empty_like(a) if want_map else None
         if train:
             d0, d1, d2 = torch.empty_like(a), torch.empty_like(a), torch.empty_like(a)
@@ -63,7 +63,7 @@ def _backward(l1_mode: int, ssim_weight: float, img1, img2, dL_dmap, uniform_cha
     a, b = _check(img1, img2)
     B, CH, H, W = a.shape
     dev = a.device
-    with torch.cuda.device(dev):
+    with _on(dev):
         if dL_dmap is not None:
             if dL_dmap.shape != a.shape or not dL_dmap.is_cuda or dL_dmap.dtype != torch.float32:
                 raise RuntimeError("fused_ssim (litegs_b200): dL_dmap must be a float32 CUDA tensor shaped like the images")
