@@ -94,61 +94,65 @@ def fusedl1ssim_loss_backward(ssim_weight, C1, C2, img1, img2, dL_dmap, dm_dmu1,
 
 
 # ---- the Python layer of the reference package (fused_ssim/fused_ssim/__init__.py:16-90) -----------------------------
+# One autograd node serves both maps; the two public Function classes only fix the mode and the reference's argument order.
 
-class FusedSSIMMap(torch.autograd.Function):
+def _crop(t, padding):
+    return t[:, :, 5:-5, 5:-5] if padding == "valid" else t
+
+
+class _MapFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, C1, C2, img1, img2, padding="same", train=True):
-        ssim_map, dm_dmu1, dm_dsigma1_sq, dm_dsigma12 = fusedssim(C1, C2, img1, img2, train)
-        if padding == "valid":
-            ssim_map = ssim_map[:, :, 5:-5, 5:-5]
-        ctx.save_for_backward(img1.detach(), img2, dm_dmu1, dm_dsigma1_sq, dm_dsigma12)
-        ctx.C1, ctx.C2, ctx.padding = C1, C2, padding
-        return ssim_map
+    def forward(ctx, l1_mode, ssim_weight, C1, C2, img1, img2, padding, train):
+        out, d0, d1, d2, _ = _forward(l1_mode, ssim_weight, C1, C2, img1, img2, bool(train))
+        ctx.save_for_backward(img1.detach(), img2, d0, d1, d2)
+        ctx.cfg = (l1_mode, ssim_weight, padding)
+        return _crop(out, padding)
 
     @staticmethod
-    def backward(ctx, opt_grad):
-        img1, img2, dm_dmu1, dm_dsigma1_sq, dm_dsigma12 = ctx.saved_tensors
-        dL_dmap = opt_grad
-        if ctx.padding == "valid":
-            dL_dmap = torch.zeros_like(img1)
-            dL_dmap[:, :, 5:-5, 5:-5] = opt_grad
-        grad = fusedssim_backward(ctx.C1, ctx.C2, img1, img2, dL_dmap, dm_dmu1, dm_dsigma1_sq, dm_dsigma12)
-        return None, None, grad, None, None, None
+    def backward(ctx, g_map):
+        img1, img2, d0, d1, d2 = ctx.saved_tensors
+        l1_mode, ssim_weight, padding = ctx.cfg
+        if padding == "valid":                      # gradient of the crop: zero border (reference __init__.py:34-37)
+            full = torch.zeros_like(img1)
+            full[:, :, 5:-5, 5:-5] = g_map
+            g_map = full
+        g = _backward(l1_mode, ssim_weight, img1, img2, g_map, 0.0, d0, d1, d2)
+        return None, None, None, None, g, None, None, None
+
+
+class FusedSSIMMap:
+    """FusedSSIMMap.apply(C1, C2, img1, img2, padding="same", train=True) -> SSIM map (reference __init__.py:16-42)."""
+
+    @staticmethod
+    def apply(C1, C2, img1, img2, padding="same", train=True):
+        return _MapFn.apply(0, 0.0, C1, C2, img1, img2, padding, train)
+
+
+class FusedL1SSIMLossMap:
+    """FusedL1SSIMLossMap.apply(ssim_weight, C1, C2, img1, img2, padding="same", train=True) -> loss map (:53-80)."""
+
+    @staticmethod
+    def apply(ssim_weight, C1, C2, img1, img2, padding="same", train=True):
+        return _MapFn.apply(1, ssim_weight, C1, C2, img1, img2, padding, train)
+
+
+def _consts():
+    return 0.01 ** 2, 0.03 ** 2
 
 
 def fused_ssim(img1, img2, padding="same", train=True):
-    C1 = 0.01 ** 2
-    C2 = 0.03 ** 2
-    assert padding in allowed_padding
-    img1 = img1.contiguous()
-    return FusedSSIMMap.apply(C1, C2, img1, img2, padding, train).mean()
-
-
-class FusedL1SSIMLossMap(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, ssim_weight, C1, C2, img1, img2, padding="same", train=True):
-        loss_map, dm_dmu1, dm_dsigma1_sq, dm_dsigma12 = fusedl1ssim_loss(ssim_weight, C1, C2, img1, img2, train)
-        if padding == "valid":
-            loss_map = loss_map[:, :, 5:-5, 5:-5]
-        ctx.save_for_backward(img1.detach(), img2, dm_dmu1, dm_dsigma1_sq, dm_dsigma12)
-        ctx.ssim_weight, ctx.C1, ctx.C2, ctx.padding = ssim_weight, C1, C2, padding
-        return loss_map
-
-    @staticmethod
-    def backward(ctx, opt_grad):
-        img1, img2, dm_dmu1, dm_dsigma1_sq, dm_dsigma12 = ctx.saved_tensors
-        dL_dmap = opt_grad
-        if ctx.padding == "valid":
-            dL_dmap = torch.zeros_like(img1)
-            dL_dmap[:, :, 5:-5, 5:-5] = opt_grad
-        grad = fusedl1ssim_loss_backward(ctx.ssim_weight, ctx.C1, ctx.C2, img1, img2, dL_dmap, dm_dmu1, dm_dsigma1_sq, dm_dsigma12)
-        return None, None, None, grad, None, None, None
+    """Mean SSIM (reference __init__.py:44-51)."""
+    if padding not in allowed_padding:
+        raise AssertionError(f"padding must be one of {allowed_padding}")
+    C1, C2 = _consts()
+    return FusedSSIMMap.apply(C1, C2, img1.contiguous(), img2, padding, train).mean()
 
 
 def fused_l1_ssim_loss(img1, img2, ssim_weight=0.2, padding="same", train=True):
-    C1 = 0.01 ** 2
-    C2 = 0.03 ** 2
-    assert padding in allowed_padding
+    """mean(w (1 - SSIM) + (1 - w) |img1 - img2|) (reference __init__.py:82-90; what trainer.py:145 calls)."""
+    if padding not in allowed_padding:
+        raise AssertionError(f"padding must be one of {allowed_padding}")
+    C1, C2 = _consts()
     return FusedL1SSIMLossMap.apply(ssim_weight, C1, C2, img1, img2, padding, train).mean()
 
 
@@ -158,8 +162,7 @@ def l1_ssim_loss_and_grad(img1, img2, ssim_weight=0.2, upstream: float = 1.0):
     """loss = mean(w (1 - SSIM) + (1 - w) |img1 - img2|) over all B*CH*H*W elements (= fused_l1_ssim_loss(img1, img2, w),
     padding "same") and upstream * dloss/dimg1, in two kernels: no loss map, no autograd graph.  Returns
     (loss f32[] on the device, dL_dimg1 f32[B,CH,H,W])."""
-    C1 = 0.01 ** 2
-    C2 = 0.03 ** 2
+    C1, C2 = _consts()
     _, d0, d1, d2, sums = _forward(1, ssim_weight, C1, C2, img1, img2, True, want_map=False, want_sums=True)
     n = img1.numel()
     loss = sums.sum(dtype=torch.float64).div_(n).to(torch.float32)      # fixed-order reduction of ~1e3 partials: deterministic
