@@ -552,7 +552,7 @@ def run_ours(args, rank, world, local_rank):
     gpu_launches = 0
     for name, (tot, n) in summ.items():
         if name in hand_written:
-            mult = {"lgs_tile_range": 2, "lgs_tile_range_u16": 2}.get(name, 1)       # fill + range kernels
+            mult = 1
             gpu_launches += n * mult
     gpu_launches += timer.sort_kernels
     line = {
