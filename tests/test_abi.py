@@ -86,3 +86,23 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.LiteGSB200Error):
         _lib.load()
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under litegs_b200/ (nor the drop-in shims, nor the example) may import it."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = [os.path.join(root, "litegs_fused.py"), os.path.join(root, "fused_ssim.py"), os.path.join(root, "examples", "train_synthetic.py")]
+    for d, _, fs in os.walk(os.path.join(root, "litegs_b200")):
+        files += [os.path.join(d, f) for f in fs if f.endswith(".py")]
+    pat = re.compile(r"^\s*(import\s+oracle\b|from\s+oracle\b)", re.M)
+    bad = [f for f in files if os.path.exists(f) and pat.search(open(f).read())]
+    assert not bad, bad
+
+
+def test_fused_ssim_shim_has_the_reference_names():
+    """fused_ssim/fused_ssim/__init__.py:5-6,16,44,53,82 and ext.cpp:4-9."""
+    import fused_ssim as m
+    for n in ("fusedssim", "fusedssim_backward", "fusedl1ssim_loss", "fusedl1ssim_loss_backward", "FusedSSIMMap", "FusedL1SSIMLossMap",
+              "fused_ssim", "fused_l1_ssim_loss", "allowed_padding"):
+        assert hasattr(m, n), n
