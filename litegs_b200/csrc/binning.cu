@@ -188,9 +188,9 @@ __global__ void __launch_bounds__(256) tile_range_kernel(const KeyT* __restrict_
     }
 }
 
-// The same table by binary search: entry t only depends on where key t would be inserted in the sorted list, so one
-// thread per tile does one lower_bound (log2 L dependent L2 hits) instead of the whole list being streamed once --
-// 16k threads x 24 loads instead of 22 MB at 1080p.  Bit-identical to tile_range_kernel (kept above as the reference
+// The same table by search: entry t only depends on where key t would be inserted in the sorted list, so one warp per
+// tile does one lower_bound instead of the whole list being streamed once -- 16k warps x 5 probe rounds instead of 22 MB at
+// 1080p.  Bit-identical to tile_range_kernel (kept above as the reference
 // form and for the description of the rules):
 //   populated t                      -> first index of t
 //   empty t right after a populated  -> that tile's end (its successor's start); for the LAST populated tile only if fix_last
@@ -200,14 +200,25 @@ template <typename KeyT>
 __global__ void __launch_bounds__(256) tile_range_bsearch_kernel(const KeyT* __restrict__ keys, int L, int max_tile, int fix_last,
                                                                  int* __restrict__ range)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    // one WARP per tile: a 32-ary search (each lane probes the last key of one of 32 segments, a ballot counts the segments
+    // that lie entirely below t) needs 5 rounds of independent loads at 1080p where a binary search needs 24 dependent ones
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), b = blockIdx.y;
     if (t > max_tile + 1) return;
     const KeyT* k = keys + (size_t)b * L;
-    int lo = 0, hi = L;                                     // lower_bound(t)
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if ((int)k[mid] < t) lo = mid + 1; else hi = mid;
+    int lo = 0, hi = L;                                     // lower_bound(t) lies in [lo, hi]
+    while (hi - lo > 32) {
+        const int stride = (hi - lo + 31) >> 5;
+        const int probe = min(hi - 1, lo + lane * stride + stride - 1);
+        const int c = __popc(__ballot_sync(0xffffffffu, (int)k[probe] < t));     // keys are sorted: the predicate is 1..1 0..0
+        lo = min(hi, lo + c * stride);
+        hi = min(hi, lo + stride);
     }
+    {
+        const bool below = lo + lane < hi && (int)k[lo + lane] < t;
+        lo += __popc(__ballot_sync(0xffffffffu, below));
+    }
+    if (lane != 0) return;
     int r = -1;
     if (lo < L && (int)k[lo] == t) r = lo;
     else if (t >= 1 && lo > 0 && (int)k[lo - 1] == t - 1 && (lo < L || fix_last)) r = lo;
@@ -238,7 +249,7 @@ static int tile_range_launch(const KeyT* keys, int V, int L, int max_tile, int f
         LGS_CHECK_LAUNCH("tile_range_kernel");
         return LGS_OK;
     }
-    tile_range_bsearch_kernel<KeyT><<<dim3(lgs_cdiv(max_tile + 2, 256), V), 256, 0, st>>>(keys, L, max_tile, fix_last, range);
+    tile_range_bsearch_kernel<KeyT><<<dim3(lgs_cdiv(max_tile + 2, 8), V), 256, 0, st>>>(keys, L, max_tile, fix_last, range);
     LGS_CHECK_LAUNCH("tile_range_bsearch_kernel");
     return LGS_OK;
 }
