@@ -106,3 +106,20 @@ def test_fused_ssim_shim_has_the_reference_names():
     for n in ("fusedssim", "fusedssim_backward", "fusedl1ssim_loss", "fusedl1ssim_loss_backward", "FusedSSIMMap", "FusedL1SSIMLossMap",
               "fused_ssim", "fused_l1_ssim_loss", "allowed_padding"):
         assert hasattr(m, n), n
+
+
+def test_no_kernel_of_ours_spills_to_local_memory():
+    """cuobjdump -res-usage: every hand-written kernel compiles without local-memory spills (LOCAL:0) and within the
+    255-register limit with room to spare (a regression here is a silent 2x slowdown of an issue-bound kernel)."""
+    import shutil
+    import subprocess
+    from litegs_b200 import _lib
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([exe, "-res-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    names = re.findall(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", out)
+    ours = [(n, int(r), int(l)) for n, r, s, sh, l in names if "cub" not in n and "thrust" not in n]
+    assert len(ours) > 60, len(ours)
+    assert all(l == 0 for _, _, l in ours), [n for n, _, l in ours if l]
+    assert max(r for _, r, _ in ours) <= 168, max(ours, key=lambda t: t[1])
