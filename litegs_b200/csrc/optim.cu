@@ -34,32 +34,33 @@ __global__ void adam_dense_kernel(AdamGroups G, float* __restrict__ grad, float*
 {
     const int c = blockIdx.x;
     if (touched != nullptr && touched[c] == 0.0f) return;
-    const int rows = G.row0[NGROUP];
     const size_t CS = (size_t)C * S;
     const size_t off = (size_t)c * S + 4 * threadIdx.x;
-    int k = 0;
-    for (int r = 0; r < rows; r++) {
-        while (r >= G.row0[k + 1]) k++;
-        const size_t f = (size_t)r * CS + off;
-        float4 g4 = *reinterpret_cast<const float4*>(grad + f);
-        float4 m4 = *reinterpret_cast<const float4*>(m + f);
-        float4 v4 = *reinterpret_cast<const float4*>(v + f);
-        float* pp = G.param[k] + (size_t)(r - G.row0[k]) * CS + off;
-        float4 p4 = *reinterpret_cast<const float4*>(pp);
-        const float lr = G.lr[k];
-        float* gp = &g4.x; float* mp = &m4.x; float* vp = &v4.x; float* pq = &p4.x;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            float g = gp[i];
-            float e1 = b1 * mp[i] + (1.0f - b1) * g;
-            float e2 = b2 * vp[i] + (1.0f - b2) * g * g;
-            pq[i] += -lr * e1 / (sqrtf(e2) + eps);
-            mp[i] = e1; vp[i] = e2;
+    for (int k = 0; k < NGROUP; k++) {          // static group index: G stays in the constant bank (no local copy of the struct)
+        const float lr = G.lr[k];
+        float* const pbase = G.param[k];
+        for (int r = G.row0[k]; r < G.row0[k + 1]; r++) {
+            const size_t f = (size_t)r * CS + off;
+            float4 g4 = *reinterpret_cast<const float4*>(grad + f);
+            float4 m4 = *reinterpret_cast<const float4*>(m + f);
+            float4 v4 = *reinterpret_cast<const float4*>(v + f);
+            float* pp = pbase + (size_t)(r - G.row0[k]) * CS + off;
+            float4 p4 = *reinterpret_cast<const float4*>(pp);
+            float* gp = &g4.x; float* mp = &m4.x; float* vp = &v4.x; float* pq = &p4.x;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                float g = gp[i];
+                float e1 = b1 * mp[i] + (1.0f - b1) * g;
+                float e2 = b2 * vp[i] + (1.0f - b2) * g * g;
+                pq[i] += -lr * e1 / (sqrtf(e2) + eps);
+                mp[i] = e1; vp[i] = e2;
+            }
+            *reinterpret_cast<float4*>(m + f) = m4;
+            *reinterpret_cast<float4*>(v + f) = v4;
+            *reinterpret_cast<float4*>(pp) = p4;
+            if (CLEAR) *reinterpret_cast<float4*>(grad + f) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        *reinterpret_cast<float4*>(m + f) = m4;
-        *reinterpret_cast<float4*>(v + f) = v4;
-        *reinterpret_cast<float4*>(pp) = p4;
-        if (CLEAR) *reinterpret_cast<float4*>(grad + f) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (CLEAR && touched != nullptr) {
         __syncthreads();
