@@ -57,7 +57,7 @@ def load_dataset(root, image_dir="images", dev=None):
         if c.model != "PINHOLE":
             continue                                     # as the reference (colmap.py:222-224)
         cam = colmap.camera_from_colmap(im.qvec, im.tvec, c.params, c.width, c.height)
-        gt = np.asarray(PIL.Image.open(os.path.join(root, image_dir, im.name)).convert("RGB"), np.uint8)
+        gt = np.array(PIL.Image.open(os.path.join(root, image_dir, im.name)).convert("RGB"), np.uint8)
         frames.append(({k: torch.from_numpy(v).to(dev) for k, v in cam.items()},
                        torch.from_numpy(gt).to(dev).permute(2, 0, 1)[None].float().div_(255.0).contiguous(), (c.height, c.width)))
     P = list(pts.values())
