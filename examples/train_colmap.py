@@ -81,8 +81,7 @@ def train(root, iters=300, views_per_step=8, log=print):
         idx = [(it * views_per_step + j) % len(frames) for j in range(views_per_step)]
         # positions and shapes move, so the chunk AABBs used for culling are refreshed from the parameters now and then
         if it % 50 == 0:
-            o, e = scene.cluster_aabb(P["xyz"].cpu().numpy(), P["scale"].cpu().numpy(), P["rot"].cpu().numpy())
-            A = [torch.from_numpy(o).to(dev), torch.from_numpy(e).to(dev)]
+            A = list(scene.cluster_aabb_torch(P["xyz"], P["scale"], P["rot"]))
         losses = render.render_views(views_per_step, lambda i: frames[idx[i]][0], None, A[0], A[1], P["xyz"], P["scale"], P["rot"],
                                      P["sh_0"], P["sh_rest"], P["opacity"], 3, (H, W), pp, acc.grads(),
                                      loss_and_grad_fn=lambda i, img: ssim.l1_ssim_loss_and_grad(img.contiguous(), frames[idx[i]][1], 0.2,

@@ -121,6 +121,25 @@ def cluster_aabb(xyz_c: np.ndarray, scale_c: np.ndarray, rot_c: np.ndarray):
     return ((hi + lo) / 2).astype(np.float32), ((hi - lo) / 2).astype(np.float32)
 
 
+def cluster_aabb_torch(xyz_c, scale_c, rot_c):
+    """cluster_aabb on torch tensors of any device (the chunk maintenance step of a training loop: positions and shapes
+    move, the culling boxes follow without a host round trip).  Same semantics, float32 -> (origin [3,C], extend [3,C])."""
+    import torch
+    C, S = xyz_c.shape[-2:]
+    xyz = xyz_c.reshape(3, -1).float()
+    s = torch.exp(scale_c.reshape(3, -1).float())
+    q = rot_c.reshape(4, -1).float()
+    q = q / q.norm(dim=0, keepdim=True)
+    r, x, y, z = q[0], q[1], q[2], q[3]
+    R = torch.stack([torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y + r * z), 2 * (x * z - r * y)]),
+                     torch.stack([2 * (x * y - r * z), 1 - 2 * (x * x + z * z), 2 * (y * z + r * x)]),
+                     torch.stack([2 * (x * z + r * y), 2 * (y * z - r * x), 1 - 2 * (x * x + y * y)])])          # [3,3,N], as quat_to_R
+    ext = (R * s[:, None, :] * math.sqrt(2 * math.log(255))).abs().sum(dim=0)
+    hi = (xyz + ext).reshape(3, C, S).amax(-1)
+    lo = (xyz - ext).reshape(3, C, S).amin(-1)
+    return ((hi + lo) * 0.5).contiguous(), ((hi - lo) * 0.5).contiguous()
+
+
 def make_scene(n: int, sh_degree: int = 3, chunk: int = 128, seed: int = 0, log_scale_range=(0.002, 0.02),
                morton: bool = True, cube: float = 1.0, sh_rest_sigma: float = 0.1):
     """Random clustered Gaussian parameters following BASELINE.md.  Returns a dict of float32 arrays

@@ -68,3 +68,15 @@ def test_ascii_ply_and_clustered_round_trip(tmp_path):
         b = back[k].reshape(*back[k].shape[:-2], -1)[..., :1000]
         assert np.array_equal(a, b), k
     assert back["cluster_origin"].shape == (3, back["xyz"].shape[-2])
+
+
+def test_chunk_aabbs_on_torch_match_the_numpy_form():
+    """scene.cluster_aabb_torch (device-agnostic, used by the training example to refresh the culling boxes) against
+    scene.cluster_aabb (reference semantics litegs/scene/cluster.py:29-46) on a random clustered scene."""
+    import torch
+    sc = scene.make_scene(3000, sh_degree=0, seed=8, log_scale_range=(0.01, 0.2))
+    o, e = scene.cluster_aabb(sc["xyz"], sc["scale"], sc["rot"])
+    to, te = scene.cluster_aabb_torch(torch.from_numpy(sc["xyz"]), torch.from_numpy(sc["scale"]), torch.from_numpy(sc["rot"]))
+    assert to.shape == o.shape and te.shape == e.shape and to.dtype == torch.float32
+    assert np.abs(to.numpy() - o).max() < 1e-5 and np.abs(te.numpy() - e).max() < 1e-5
+    assert np.array_equal(sc["cluster_origin"], o) and np.array_equal(sc["cluster_extend"], e)
