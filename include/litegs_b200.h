@@ -252,7 +252,7 @@ int lgs_adam_step_dense(float* const* params, const int* rows_per_param, const f
                         float* exp_avg, float* exp_avg_sq, float* touched, int C, int S, double b1, double b2, double eps,
                         int clear_grad, void* stream);
 
-/* gpu_driven_pipeline_sparse_op, GR/compact.cu:1221-1336 (GR/compact.h:35-41). dtype 0=f32 1=i32; op 0=add 1=min 2=max */
+/* gpu_driven_pipeline_sparse_op, GR/compact.cu:1221-1336 (GR/compact.h:30-36). dtype 0=f32 1=i32; op 0=add 1=min 2=max */
 int lgs_sparse_chunk_op(void* A, const void* B, const int64_t* visible_chunk_ids, const int* visible_count, int dtype,
                         int op, int ele_num, int chunks, int alloc_chunks, int chunk_size, void* stream);
 

@@ -6,7 +6,7 @@ eps 1e-15, betas 0.9/0.999, only visible chunks update).  Here the gradients of 
 dense buffer (``dist.GradAccumulator``, all-reduced over ranks), so the step is ONE kernel over all six tensors
 (csrc/optim.cu) that also clears the consumed gradient rows and chunk marks.
 
-``get_optimizer`` mirrors the reference's group layout and learning rates (optimizer.py:74-97); ``Scheduler`` is its
+``get_optimizer`` mirrors the reference's group layout and learning rates (optimizer.py:74-95); ``Scheduler`` is its
 log-linear position learning-rate schedule (optimizer.py:46-72).
 """
 from __future__ import annotations
@@ -88,7 +88,7 @@ class Scheduler:
 
 def get_optimizer(params: Dict[str, torch.Tensor], spatial_lr_scale: float, position_lr_init=0.00016, position_lr_final=0.0000016,
                   position_lr_max_steps=30000, feature_lr=0.0025, opacity_lr=0.025, scaling_lr=0.005, rotation_lr=0.001):
-    """optimizer.py:74-97 with the reference's default OptimizationParams (arguments.py:82-88)."""
+    """optimizer.py:74-95 with the reference's default OptimizationParams (arguments.py:82-88)."""
     lr = {"xyz": position_lr_init * spatial_lr_scale, "sh_0": feature_lr, "sh_rest": feature_lr / 10.0, "opacity": opacity_lr,
           "scale": scaling_lr, "rot": rotation_lr}
     opt = FusedAdam(params, lr, eps=1e-15)

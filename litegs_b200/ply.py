@@ -82,7 +82,7 @@ def _read_vertex_table(path: str):
 
 def load_ply(path: str, sh_degree: int):
     """-> xyz [3,N], scale [3,N], rot [4,N], sh_0 [1,3,N], sh_rest [K-1,3,N], opacity [1,N]  (float32), the reference's
-    return order (ply.py:47-90).  Files with fewer SH bands than sh_degree are zero-extended; more is an error."""
+    return order (ply.py:47-87).  Files with fewer SH bands than sh_degree are zero-extended; more is an error."""
     t = _read_vertex_table(path)
     n = t.shape[0]
     col = lambda name: np.asarray(t[name], np.float32)
