@@ -39,7 +39,7 @@ int lgs_abi_version(void);
 
 /* ---- chunk culling + activation ------------------------------------------------------------------ */
 
-/* replaces frustum_culling_aabb, GR/compact.cu:419-551 (GR/compact.h:33).
+/* replaces frustum_culling_aabb, GR/compact.cu:419-551 (GR/compact.h:28).
  * aabb_origin/aabb_ext f32[3,M]; frustumplane f32[V,6,4]; visibility u8[M]; visible_num i32[1];
  * visible_chunk_id i64[M] receives the visible chunk ids in ASCENDING order (first *visible_num valid). */
 int lgs_frustum_culling_aabb(const float* aabb_origin, const float* aabb_ext, const float* frustumplane, int M, int V,
@@ -70,7 +70,7 @@ int lgs_activate_backward(int sh_degree, const int64_t* visible_chunk_id, const 
 
 /* ---- per-Gaussian projection operators ------------------------------------------------------------- */
 
-/* mvp_transform_forward/backward, GR/transform.cu:378-598 (GR/transform.h:13-18). world f32[4,N] ->
+/* mvp_transform_forward/backward, GR/transform.cu:378-598 (GR/transform.h:11-16). world f32[4,N] ->
  * view,ndc f32[V,4,N]; backward sums over views into f32[4,N]. */
 int lgs_mvp_transform_forward(const float* world_position, const float* view_matrix, const float* proj_matrix,
                               const int* valid_length, int V, int N, float* view_position, float* ndc_position, void* stream);
@@ -78,7 +78,7 @@ int lgs_mvp_transform_backward(const float* grad_ndc_pos, const float* grad_view
                                const float* proj_matrix, const float* view_pos, const int* valid_length, int V, int N,
                                float* grad_world_pos, void* stream);
 
-/* createTransformMatrix_forward/backward, GR/transform.cu:92-256 (GR/transform.h:6-7). quaternion f32[4,N]
+/* createTransformMatrix_forward/backward, GR/transform.cu:92-256 (GR/transform.h:5-6). quaternion f32[4,N]
  * (r,x,y,z), scale f32[3,N] -> T = diag(s) R(q) f32[3,3,N]. */
 int lgs_create_transform_matrix_forward(const float* quaternion, const float* scale, const int* valid_length, int N,
                                         float* transform, void* stream);
@@ -86,25 +86,25 @@ int lgs_create_transform_matrix_backward(const float* transform_grad, const floa
                                          const int* valid_length, int N, float* grad_quaternion, float* grad_scale,
                                          void* stream);
 
-/* jacobianRayspace, GR/transform.cu:22-90 (GR/transform.h:4). view_pos f32[V,4,N] -> J f32[V,3,3,N]
+/* jacobianRayspace, GR/transform.cu:22-90 (GR/transform.h:3). view_pos f32[V,4,N] -> J f32[V,3,3,N]
  * (all nine rows written, five of them zero). */
 int lgs_jacobian_rayspace(const float* view_pos, const float* proj_matrix, const int* valid_length, int V, int N,
                           int output_h, int output_w, float* jacobian, void* stream);
 
-/* createCov2dDirectly_forward/backward, GR/transform.cu:736-927 (GR/transform.h:21-22). */
+/* createCov2dDirectly_forward/backward, GR/transform.cu:736-927 (GR/transform.h:19-20). */
 int lgs_create_cov2d_forward(const float* J, const float* view_matrix, const float* transform_matrix,
                              const int* valid_length, int V, int N, float* cov2d, void* stream);
 int lgs_create_cov2d_backward(const float* cov2d_grad, const float* J, const float* view_matrix,
                               const float* transform_matrix, const int* valid_length, int V, int N,
                               float* transform_matrix_grad, void* stream);
 
-/* eigh_and_inv_2x2matrix_forward / inv_2x2matrix_backward, GR/transform.cu:1364-1518 (GR/transform.h:24-25). */
+/* eigh_and_inv_2x2matrix_forward / inv_2x2matrix_backward, GR/transform.cu:1364-1518 (GR/transform.h:25-26). */
 int lgs_eigh_and_inv_2x2_forward(const float* input, const int* valid_length, int V, int N, float* val, float* vec,
                                  float* inv, void* stream);
 int lgs_inv_2x2_backward(const float* inv_matrix, const float* grad_inv, const int* valid_length, int V, int N,
                          float* grad_matrix, void* stream);
 
-/* sh2rgb_forward/backward, GR/transform.cu:951-1361 (GR/transform.h:23-24): cluster_size=0 path. */
+/* sh2rgb_forward/backward, GR/transform.cu:951-1361 (GR/transform.h:22-23): cluster_size=0 path. */
 int lgs_sh2rgb_forward(int degree, const float* sh_base, const float* sh_rest, const float* dirs, int V, int N,
                        float* rgb, void* stream);
 int lgs_sh2rgb_backward(int degree, const float* rgb_grad, int sh_rest_dim, const float* dirs, int V, int N,
@@ -112,7 +112,7 @@ int lgs_sh2rgb_backward(int degree, const float* rgb_grad, int sh_rest_dim, cons
 
 /* ---- binning ----------------------------------------------------------------------------------------- */
 
-/* get_allocate_size, GR/binning.cu:289-440 (GR/binning.h:10-14): visibility + exact ellipse/tile overlap
+/* get_allocate_size, GR/binning.cu:289-440 (GR/binning.h:11-15): visibility + exact ellipse/tile overlap
  * count (GR/speedy_splat.cuh:33-149). left_up/right_down i32[V,2,N], allocate_size i32[V,N] (zeroed). */
 int lgs_get_allocate_size(const float* ndc, const float* view_space_z, const float* inv_cov2d, const float* opacity,
                           const int* valid_length, int V, int N, int height, int width, int tile_h, int tile_w,
@@ -128,7 +128,7 @@ int lgs_create_table(const float* ndc, const float* inv_cov2d, const float* opac
                      int tile_w, int* sorted_tile_id, int* sorted_point_id, void* workspace, size_t workspace_bytes,
                      void* stream);
 
-/* tileRange, GR/binning.cu:228-287 (GR/binning.h:9). tile_range i32[V,max_tile_id+2], -1 = empty.
+/* tileRange, GR/binning.cu:228-287 (GR/binning.h:10). tile_range i32[V,max_tile_id+2], -1 = empty.
  * fix_last=1 closes the last populated tile (the reference leaves it open: SURVEY Q3); 0 = bit-compatible. */
 int lgs_tile_range(const int* table_tile_id, int V, int table_length, int max_tile_id, int fix_last, int* tile_range,
                    void* stream);
@@ -160,7 +160,7 @@ int lgs_scan_gathered(const int* counts, const unsigned* order, int n, int* out,
 int lgs_pack_params(const float* ndc, const float* cov2d_inv, const float* color, const float* opacity, int V, int N,
                     int img_h, int img_w, float* packed_params, void* stream);
 
-/* rasterize_forward(_packed), GR/raster.cu:161-332,386-586 (GR/raster.h:3-33).  Images are padded to
+/* rasterize_forward(_packed), GR/raster.cu:161-332,386-586 (GR/raster.h:3-32).  Images are padded to
  * whole tiles: img f32[V,3,Hp,Wp], transmittance f32[V,1,Hp,Wp], last_contributor i16[V,1,Hp,Wp];
  * fragment_count i32[V,1,N] / fragment_weight f32[V,1,N] are accumulated when enable_statistic (caller
  * zeroes them).  specific_tiles i32[V,n_specific] (1-based tile ids, 0 = skip) or NULL.  clamp_zero=0 writes
@@ -172,7 +172,7 @@ int lgs_rasterize_forward_packed(const int* sorted_points, const int* start_inde
                                  float* transmittance, short* last_contributor, int* fragment_count,
                                  float* fragment_weight, void* stream);
 
-/* rasterize_backward, GR/raster.cu:599-886,917-1037 (GR/raster.h:35-50).  packed_grad f32[V,N,12] is
+/* rasterize_backward, GR/raster.cu:599-886,917-1037 (GR/raster.h:34-50).  packed_grad f32[V,N,12] is
  * scratch (zeroed here); d_trans_img, clamped_img (the forward's clamp_zero=1 output: blocks the gradient where a
  * colour was clamped up to 0) and grad_inv_scaler (DEVICE f32[1]) may be NULL.  Outputs d_ndc
  * f32[V,4,N], d_cov2d_inv f32[V,2,2,N], d_color f32[V,3,N], d_opacity f32[1,N] (view 0 only, as the
