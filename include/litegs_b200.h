@@ -32,7 +32,9 @@ extern "C" {
 #define LGS_ERR_ARG 10001
 #define LGS_ERR_WORKSPACE 10002
 #define LGS_REC_FLOATS 12  /* floats per packed splat record  (px py A B | C o r g | b depth - -) */
-#define LGS_GRAD_FLOATS 12 /* floats per gradient accumulator (dmx dmy dA dB | dC dr dg db | do esq - -) */
+#define LGS_GRAD_FLOATS 12 /* floats per gradient accumulator: raw moments of dL/dpower over the splat's pixels
+                              (sum dx*s0, sum s1, sum dx^2*s0, sum dx*s1 | sum s2, dr, dg, db | sum s0, err_sq, -, -);
+                              the consumers (unpack inside lgs_rasterize_backward, lgs_project_backward) apply the conic */
 
 const char* lgs_last_error(void);
 int lgs_abi_version(void);
@@ -165,12 +167,20 @@ int lgs_pack_params(const float* ndc, const float* cov2d_inv, const float* color
  * fragment_count i32[V,1,N] / fragment_weight f32[V,1,N] are accumulated when enable_statistic (caller
  * zeroes them).  specific_tiles i32[V,n_specific] (1-based tile ids, 0 = skip) or NULL.  clamp_zero=0 writes
  * min(c,1) as the reference kernel does; 1 writes clamp(c,0,1), i.e. also the clamp render() applies in Python
- * (render/__init__.py:87) -- then pass the image back to lgs_rasterize_backward as `clamped_img`. */
+ * (render/__init__.py:87) -- then pass the image back to lgs_rasterize_backward as `clamped_img`.
+ * last_contributor holds an UNSIGNED 16-bit count (the reference reads it back as unsigned short, GR/raster.cu:683-686),
+ * saturated at 65535.  tile_work i32[V,tiles] (nullable): per tile, the deepest list position any of its pixels consumed
+ * = the backward's trip count, input of lgs_tile_order (zero it first when specific_tiles is given). */
 int lgs_rasterize_forward_packed(const int* sorted_points, const int* start_index, const float* packed_params,
                                  const int* specific_tiles, int n_specific, int V, int N, int cap, int img_h, int img_w,
                                  int tile_h, int tile_w, int enable_statistic, int clamp_zero, float* img,
                                  float* transmittance, short* last_contributor, int* fragment_count,
-                                 float* fragment_weight, void* stream);
+                                 float* fragment_weight, int* tile_work, void* stream);
+
+/* order i32[V,tiles] = 1-based tile ids by descending work (heaviest lists first), to be passed as specific_tiles:
+ * the device-side form of the reference's tile scheduling by last epoch's blend count (render/__init__.py:75-79,
+ * utils/statistic_helper.py:68-79). */
+int lgs_tile_order(const int* work, int V, int ntile, int* order, void* stream);
 
 /* rasterize_backward, GR/raster.cu:599-886,917-1037 (GR/raster.h:34-50).  packed_grad f32[V,N,12] is
  * scratch (zeroed here); d_trans_img, clamped_img (the forward's clamp_zero=1 output: blocks the gradient where a
@@ -191,6 +201,11 @@ int lgs_set_staging(int bulk);
 int lgs_set_backward_reduce(int deferred);
 /* tiles (warps) per CTA of the raster kernels: 1, 2 or 4 (default 4, env LGS_WPB) */
 int lgs_set_warps_per_block(int wpb);
+/* backward kernel: 2 = packed-pair (fma.rn.f32x2), branch-free pixel body (default); 1 = scalar kernel.  env LGS_BWD=v1|v2 */
+int lgs_set_backward_kernel(int version);
+/* err_square_sum under enable_statistic: 1 = the reference's lane-running recurrence (GR/raster.cu:779-784, default),
+ * 0 = sum over pixels of (G dalpha)^2 */
+int lgs_set_err_square_mode(int mode);
 
 /* ---- fused per-view pipeline ("Level B") ---------------------------------------------------------------- */
 

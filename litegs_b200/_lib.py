@@ -44,13 +44,16 @@ SIGNATURES = {
     "lgs_scan_gathered_workspace_bytes": [_I, ctypes.POINTER(_Z)],
     "lgs_scan_gathered": [_P, _P, _I, _P, _P, _Z, _P],
     "lgs_pack_params": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
-    "lgs_rasterize_forward_packed": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    "lgs_rasterize_forward_packed": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "lgs_tile_order": [_P, _I, _I, _P, _P],
     "lgs_rasterize_backward": [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I,
                                _P, _P, _P, _P, _P, _P, _P, _P],
     "lgs_set_staging": [_I],
     "lgs_set_sort_impl": [_I],
     "lgs_set_warps_per_block": [_I],
     "lgs_set_backward_reduce": [_I],
+    "lgs_set_backward_kernel": [_I],
+    "lgs_set_err_square_mode": [_I],
     "lgs_project_forward": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "lgs_emit_pairs": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "lgs_project_backward": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I,

@@ -61,6 +61,23 @@ struct __align__(16) SplatRec {
 static_assert(sizeof(SplatRec) == 48, "SplatRec must be 48 bytes");
 #define LGS_REC_FLOATS 12
 
-// 12-float gradient accumulator, same indexing as raster_backward's RED targets.
-// 0:dmu_x 1:dmu_y 2:dA 3:dB(total) 4:dC 5:dr 6:dg 7:db 8:do 9:err_sq 10,11: unused
+// 12-float gradient accumulator, same indexing as raster_backward's RED targets.  The geometry slots hold RAW moments
+// of dL/dpower over the splat's pixels (dx = mu_x - x_pixel, dy = mu_y - y_pixel, s_k = sum_pixels dpw dy^k per column):
+//   0: sum dx s0   1: sum s1   2: sum dx^2 s0   3: sum dx s1   4: sum s2   5,6,7: d colour   8: sum s0   9: err_sq
+// and the consumer (unpack_kernel / project_backward_kernel) turns them into the gradients of GR/raster.cu:826-841 with the
+// splat's conic (A, B, C) and opacity o once per splat:
+//   dmu_x = -(A m0 + B m1)  dmu_y = -(B m0 + C m1)  dA = -m2/2  dB(total) = -m3  dC = -m4/2  do = m8 / o
 #define LGS_GRAD_FLOATS 12
+struct LgsRasterGrad { float dmx, dmy, dA, dB, dC, dop; };
+#ifdef __CUDACC__
+__device__ __forceinline__ void lgs_finish_raster_grad(const float4& a, const float4& c, const float4& e, float A, float B, float C,
+                                                       float o, LgsRasterGrad& g)
+{
+    g.dmx = -(A * a.x + B * a.y);
+    g.dmy = -(B * a.x + C * a.y);
+    g.dA = -0.5f * a.z;
+    g.dB = -a.w;
+    g.dC = -0.5f * c.x;
+    g.dop = (o > 0.0f) ? e.x / o : 0.0f;
+}
+#endif

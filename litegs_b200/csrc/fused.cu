@@ -316,11 +316,13 @@ __global__ void project_backward_kernel(
         const float o_raw = opac[src];
         ProjIntermediates t;
         project_chain(view, proj, p, sr_, q, o_raw, H, W, t);
-        // unpack (GR/raster.cu:870-884)
-        const float d_ndcx = ga.x * 0.5f * W * sc, d_ndcy = ga.y * 0.5f * H * sc;
-        const float dA = ga.z * sc, dBh = ga.w * 0.5f * sc, dC = gb.x * sc;
+        // raw moments -> record gradient (GR/raster.cu:826-841), then unpack (GR/raster.cu:870-884)
+        LgsRasterGrad rgd;
+        lgs_finish_raster_grad(ga, gb, gc, t.inv[0], t.inv[1], t.inv[2], t.o, rgd);
+        const float d_ndcx = rgd.dmx * 0.5f * W * sc, d_ndcy = rgd.dmy * 0.5f * H * sc;
+        const float dA = rgd.dA * sc, dBh = rgd.dB * 0.5f * sc, dC = rgd.dC * sc;
         const float dcol[3] = { gb.y * sc, gb.z * sc, gb.w * sc };
-        const float d_o = gc.x * sc;
+        const float d_o = rgd.dop * sc;
         // inverse backward: dCov = -(inv . dInv . inv) (GR/transform.cu:1446-1450), NaN -> 0
         const float iA = t.inv[0], iB = t.inv[1], iC = t.inv[2];
         float t00 = iA * dA + iB * dBh, t01 = iA * dBh + iB * dC, t10 = iB * dA + iC * dBh, t11 = iB * dBh + iC * dC;

@@ -18,6 +18,12 @@
 //    matrix (default: 9 conflict-free STS per splat, every 3 splats 27 lanes each add up one row with
 //    8 LDS.128) or a 9-shuffle transposing butterfly -- and leave the SM exactly once, as one
 //    RED.ADD.F32 per value touching a single 48-byte record.
+//  * backward v2 (default): the per-pixel math runs on PAIRS of pixels with packed fp32 (fma/mul/add.rn.f32x2 ->
+//    FFMA2/FMUL2/FADD2: one issue slot per two lanes of work), the "does this splat touch this pixel" test zeroes the
+//    Gaussian weight instead of branching around the body (every lane executes straight-line code), the 9 values that
+//    leave the warp are RAW moments (sum dx*s0, sum s1, sum dx^2*s0, sum dx*s1, sum s2, colour, sum s0) whose conic
+//    factors are applied once per splat by the consumer (unpack / project_backward) instead of once per (tile, splat, lane),
+//    and tiles are launched heaviest-first from the forward's per-tile contributor count.
 #include "common.cuh"
 
 #define FULL_MASK 0xffffffffu
@@ -191,9 +197,9 @@ __global__ void pack_kernel(const float* __restrict__ ndc, const float* __restri
 template <int TH, int TW, bool STAT, bool BULK>
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_forward_kernel(
     const int* __restrict__ sorted, const int* __restrict__ start_index, const SplatRec* __restrict__ recs,
-    const int* __restrict__ tiles, int n_sel, float* __restrict__ img, float* __restrict__ Tout, short* __restrict__ last,
-    int* __restrict__ frag_count, float* __restrict__ frag_weight, int gx, int ntile, int cap, int N, int Hp, int Wp,
-    int clamp_zero)
+    const int* __restrict__ tiles, int n_sel, float* __restrict__ img, float* __restrict__ Tout, unsigned short* __restrict__ last,
+    int* __restrict__ frag_count, float* __restrict__ frag_weight, int* __restrict__ tile_work, int gx, int ntile, int cap, int N,
+    int Hp, int Wp, int clamp_zero)
 {
     constexpr int PPT = TH * TW / 32;
     __shared__ __align__(128) SplatRec s_rec[WARPS_PER_BLOCK][2][32];
@@ -303,7 +309,17 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_forward_kernel(
         img[((size_t)b * 3 + 1) * plane + po] = fmaxf(fminf(Cg[j], 1.0f), lo);
         img[((size_t)b * 3 + 2) * plane + po] = fmaxf(fminf(Cb[j], 1.0f), lo);
         Tout[(size_t)b * plane + po] = Ts[j] * KS;
-        last[(size_t)b * plane + po] = (short)(int)nf[j];
+        // the contributor count is a 16-bit tensor in the reference contract (read back as unsigned short,
+        // GR/raster.cu:683-686): saturate instead of wrapping when a pixel stays active past 65535 list entries
+        last[(size_t)b * plane + po] = (unsigned short)__float2uint_rn(fminf(nf[j], 65535.0f));
+    }
+    if (tile_work != nullptr) {
+        // deepest list position any pixel of the tile consumed = the backward's trip count for this tile
+        float m = nf[0];
+#pragma unroll
+        for (int j = 1; j < PPT; j++) m = fmaxf(m, nf[j]);
+        const int mi = __reduce_max_sync(FULL_MASK, (int)fminf(m, 65535.0f));
+        if (lane == 0) tile_work[(size_t)b * ntile + tile_id - 1] = mi;
     }
 }
 
@@ -342,12 +358,13 @@ __device__ __forceinline__ float butterfly8(const float (&v)[8], int lane)
 template <int TH, int TW, bool STAT, bool TRANS, bool BULK, bool DEFER>
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_kernel(
     const int* __restrict__ sorted, const int* __restrict__ start_index, const SplatRec* __restrict__ recs,
-    const int* __restrict__ tiles, int n_sel, const float* __restrict__ Tfinal, const short* __restrict__ last,
+    const int* __restrict__ tiles, int n_sel, const float* __restrict__ Tfinal, const unsigned short* __restrict__ last,
     const float* __restrict__ d_img, const float* __restrict__ d_trans, const float* __restrict__ clamped_img,
     float* __restrict__ grad, int gx, int ntile, int cap, int N, int Hp, int Wp)
 {
     constexpr int PPT = TH * TW / 32;
     constexpr int NV = STAT ? 10 : 9;                       // values reduced per (tile, splat)
+    constexpr float KS = 256.0f / 255.0f, A_MIN_S = ALPHA_MIN * KS;
     __shared__ __align__(128) SplatRec s_rec[WARPS_PER_BLOCK][2][32];
     __shared__ __align__(8) uint64_t s_bar[WARPS_PER_BLOCK][2];
     __shared__ __align__(16) float s_acc[DEFER ? WARPS_PER_BLOCK : 1][DEFER ? LGS_RG * NV : 1][LGS_ROWF];
@@ -391,7 +408,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_kernel(
         }
         gt[j] = TRANS ? d_trans[(size_t)b * plane + po] * T[j] : 0.0f;   // dL/dT_final * T_final
         S[j] = 0.0f;
-        nl[j] = (int)last[(size_t)b * plane + po];
+        nl[j] = (int)last[(size_t)b * plane + po];      // unsigned 16-bit, as the reference reads it (GR/raster.cu:683-686)
         kmax = max(kmax, nl[j]);
     }
     kmax = __reduce_max_sync(FULL_MASK, kmax);
@@ -442,7 +459,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_kernel(
             const float dx = q0.x - fx, dy0 = q0.y - fy0;
             const float a2 = (-0.5f * LOG2E) * q0.z, b2 = (-LOG2E) * q0.w, c2 = (-0.5f * LOG2E) * q1.x;
             const float base = a2 * dx * dx, lin = b2 * dx;
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, dr = 0.f, dg = 0.f, db = 0.f, dop = 0.f, esq = 0.f;
+            const float os = q1.y * KS;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, dr = 0.f, dg = 0.f, db = 0.f, esq = 0.f;
             bool any = false;
 #pragma unroll
             for (int j = 0; j < PPT; j++) {
@@ -450,7 +468,9 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_kernel(
                 const float pw = fmaf(dy, fmaf(c2, dy, lin), base);
                 const float G = fast_ex2(pw);
                 const float at = q1.y * G;
-                if (k < nl[j] && at >= ALPHA_MIN) {
+                // the contribution test is the forward's expression bit for bit (os * G >= A_MIN_S, raster_forward_kernel):
+                // a splat the forward blended is never skipped here and vice versa
+                if (k < nl[j] && os * G >= A_MIN_S) {
                     any = true;
                     const float a = fminf(at, ALPHA_MAX);
                     const float rc = fast_rcp(1.0f - a);
@@ -462,21 +482,22 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_kernel(
                     float da = Tj * diff;
                     if (TRANS) da -= gt[j] * rc;
                     S[j] = fmaf(a, diff, S[j]);
-                    const float go = G * da;
-                    dop += go;
-                    if (STAT) esq = fmaf(go, go, esq);
+                    if (STAT) { const float go = G * da; esq = fmaf(go, go, esq); }
                     const float dpw = at * da;          // passes through the 255/256 clamp (GR/raster.cu:776-778)
                     s0 += dpw; s1 = fmaf(dpw, dy, s1); s2 = fmaf(dpw * dy, dy, s2);
                 }
             }
             if (__any_sync(FULL_MASK, any)) {
+                // raw moments (LGS_GRAD_* slots, common.cuh): the conic factors are applied once per splat by the consumer
                 float v8[8];
-                v8[0] = -(q0.z * dx * s0 + q0.w * s1);     // d mu_x
-                v8[1] = -(q0.w * dx * s0 + q1.x * s1);     // d mu_y
-                v8[2] = -0.5f * dx * dx * s0;              // d A
-                v8[3] = -dx * s1;                          // d B (total)
-                v8[4] = -0.5f * s2;                        // d C
+                const float u0 = dx * s0;
+                v8[0] = u0;                                // sum dx s0
+                v8[1] = s1;                                // sum s1
+                v8[2] = dx * u0;                           // sum dx^2 s0
+                v8[3] = dx * s1;                           // sum dx s1
+                v8[4] = s2;                                // sum s2
                 v8[5] = dr; v8[6] = dg; v8[7] = db;
+                float dop = s0;                            // sum s0  (d opacity = sum s0 / o)
                 const int pid = __shfl_sync(FULL_MASK, id_this, kk);
                 if (DEFER) {
                     float* row = &s_acc[DEFER ? warp : 0][DEFER ? pend * NV : 0][lane];
@@ -509,11 +530,211 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_kernel(
     st.drain();
 }
 
+// ---- backward v2: packed fp32 pairs, branch-free pixel body ----------------------------------------------------------
+// Same tiling, staging, chunk walk and shared-memory transposed reduction as raster_backward_kernel<.., DEFER=true>, with
+//  * a lane's PPT pixels handled as PPT/2 PAIRS held in float2 registers; every add/mul/fma of the per-pixel chain is one
+//    packed instruction for the pair (FADD2/FMUL2/FFMA2: half the issue slots of the scalar chain, which is what bounds
+//    this kernel -- profiles/ncu_raster_r1b_8x16_cpasync.txt: issue slots busy 79 %, DRAM 1.5 %);
+//  * no branch around the pixel body: a pixel the splat does not reach (alpha below 1/256, or the pixel had already
+//    stopped before this list position) gets its Gaussian weight G forced to 0, which makes every term of the chain an
+//    exact no-op (a = 0, 1/(1-a) = 1, T and S unchanged, all gradient terms +0);
+//  * d opacity = sum(G dalpha) = sum(dpw) / o, so the ninth reduced value is the s0 moment itself;
+//  * the transposed row sums of the flush use packed adds on the LDS.128 pairs.
+// STAT adds the densification error term in one of two forms (err_mode): 1 = the reference's lane-running recurrence
+// (GR/raster.cu:779-784: after each executed pixel PAIR the lane's running sum of G dalpha over its even rows and over its
+// odd rows is squared and added), 0 = sum over pixels of (G dalpha)^2.
+__device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
+
+template <int TH, int TW, bool STAT, bool TRANS>
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_v2_kernel(
+    const int* __restrict__ sorted, const int* __restrict__ start_index, const SplatRec* __restrict__ recs,
+    const int* __restrict__ tiles, int n_sel, const float* __restrict__ Tfinal, const unsigned short* __restrict__ last,
+    const float* __restrict__ d_img, const float* __restrict__ d_trans, const float* __restrict__ clamped_img,
+    float* __restrict__ grad, int gx, int ntile, int cap, int N, int Hp, int Wp, int err_mode)
+{
+    constexpr int PPT = TH * TW / 32, NP = PPT / 2;
+    static_assert(PPT % 2 == 0, "pixels per lane must pair up");
+    constexpr int NV = STAT ? 10 : 9;                       // values reduced per (tile, splat)
+    constexpr float KS = 256.0f / 255.0f, A_MIN_S = ALPHA_MIN * KS;
+    __shared__ __align__(128) SplatRec s_rec[WARPS_PER_BLOCK][2][32];
+    __shared__ __align__(8) uint64_t s_bar[WARPS_PER_BLOCK][2];
+    __shared__ __align__(16) float s_acc[WARPS_PER_BLOCK][LGS_RG * NV][LGS_ROWF];
+    const int lane = threadIdx.x, warp = threadIdx.y, b = blockIdx.y;
+    const int slot = blockIdx.x * blockDim.y + warp;
+    int tile_id;
+    if (tiles != nullptr) tile_id = (slot < n_sel) ? tiles[(size_t)b * n_sel + slot] : 0;
+    else tile_id = slot + 1;
+    if (tile_id <= 0 || tile_id > ntile) return;
+    const int* rg = start_index + (size_t)b * (ntile + 2);
+    const int start = rg[tile_id];
+    if (start < 0) return;
+    recs += (size_t)b * N;
+    grad += (size_t)b * N * LGS_GRAD_FLOATS;
+    const int* ids = sorted + (size_t)b * cap + start;
+
+    const int x = ((tile_id - 1) % gx) * TW + lane % TW;
+    const int y0 = ((tile_id - 1) / gx) * TH + (lane / TW) * PPT;
+    const float fx = (float)x, fy0 = (float)y0;
+    const size_t plane = (size_t)Hp * Wp;
+
+    float2 T[NP], g0[NP], g1[NP], g2[NP], S[NP], ngt[NP];
+    int nl[PPT];
+    int kmax = 0;
+#pragma unroll
+    for (int j = 0; j < PPT; j++) {
+        const size_t po = (size_t)(y0 + j) * Wp + x;
+        float t = Tfinal[(size_t)b * plane + po];
+        float a0 = d_img[((size_t)b * 3 + 0) * plane + po];
+        float a1 = d_img[((size_t)b * 3 + 1) * plane + po];
+        float a2 = d_img[((size_t)b * 3 + 2) * plane + po];
+        if (clamped_img != nullptr) {                        // backward of the fused clamp(0,1), see raster_backward_kernel
+            if (!(clamped_img[((size_t)b * 3 + 0) * plane + po] > 0.0f)) a0 = 0.0f;
+            if (!(clamped_img[((size_t)b * 3 + 1) * plane + po] > 0.0f)) a1 = 0.0f;
+            if (!(clamped_img[((size_t)b * 3 + 2) * plane + po] > 0.0f)) a2 = 0.0f;
+        }
+        const float gtj = TRANS ? -(d_trans[(size_t)b * plane + po] * t) : 0.0f;   // -(dL/dT_final * T_final)
+        if (j & 1) { T[j / 2].y = t; g0[j / 2].y = a0; g1[j / 2].y = a1; g2[j / 2].y = a2; ngt[j / 2].y = gtj; S[j / 2].y = 0.f; }
+        else       { T[j / 2].x = t; g0[j / 2].x = a0; g1[j / 2].x = a1; g2[j / 2].x = a2; ngt[j / 2].x = gtj; S[j / 2].x = 0.f; }
+        nl[j] = (int)last[(size_t)b * plane + po];           // unsigned 16-bit, as the reference reads it (GR/raster.cu:683-686)
+        kmax = max(kmax, nl[j]);
+    }
+    kmax = __reduce_max_sync(FULL_MASK, kmax);
+    if (kmax <= 0) return;
+
+    int pend = 0, pid0 = 0, pid1 = 0, pid2 = 0;        // splats parked in s_acc and their ids (warp-uniform)
+    auto flush = [&]() {
+        __syncwarp();
+        if (lane < pend * NV) {
+            const float4* r4 = reinterpret_cast<const float4*>(&s_acc[warp][lane][0]);
+            const float4 x0 = r4[0], x1 = r4[1], x2 = r4[2], x3 = r4[3], x4 = r4[4], x5 = r4[5], x6 = r4[6], x7 = r4[7];
+            float2 p0 = __fadd2_rn(make_float2(x0.x, x0.y), make_float2(x0.z, x0.w));
+            float2 p1 = __fadd2_rn(make_float2(x1.x, x1.y), make_float2(x1.z, x1.w));
+            float2 p2 = __fadd2_rn(make_float2(x2.x, x2.y), make_float2(x2.z, x2.w));
+            float2 p3 = __fadd2_rn(make_float2(x3.x, x3.y), make_float2(x3.z, x3.w));
+            float2 p4 = __fadd2_rn(make_float2(x4.x, x4.y), make_float2(x4.z, x4.w));
+            float2 p5 = __fadd2_rn(make_float2(x5.x, x5.y), make_float2(x5.z, x5.w));
+            float2 p6 = __fadd2_rn(make_float2(x6.x, x6.y), make_float2(x6.z, x6.w));
+            float2 p7 = __fadd2_rn(make_float2(x7.x, x7.y), make_float2(x7.z, x7.w));
+            p0 = __fadd2_rn(p0, p1); p2 = __fadd2_rn(p2, p3); p4 = __fadd2_rn(p4, p5); p6 = __fadd2_rn(p6, p7);
+            p0 = __fadd2_rn(p0, p2); p4 = __fadd2_rn(p4, p6);
+            p0 = __fadd2_rn(p0, p4);
+            const float sum = p0.x + p0.y;
+            const int sp = lane / NV, v = lane - sp * NV;
+            const int pid = sp == 0 ? pid0 : (sp == 1 ? pid1 : pid2);
+            atomicAdd(&grad[(size_t)pid * LGS_GRAD_FLOATS + v], sum);                            // RED.ADD.F32
+        }
+        __syncwarp();
+        pend = 0;
+    };
+    Stager<false> st;
+    st.init(&s_rec[warp][0][0], &s_bar[warp][0], lane);
+    const int nchunks = (kmax + 31) >> 5;
+    int c0 = nchunks - 1;
+    int id_cur = (c0 * 32 + lane < kmax) ? ids[c0 * 32 + lane] : -1;
+    st.issue(0, recs, id_cur);
+    int id_next = (c0 >= 1) ? ids[(c0 - 1) * 32 + lane] : -1;
+    for (int v = 0; v < nchunks; v++) {
+        const int c = nchunks - 1 - v;
+        const bool more = (c >= 1);
+        const int id_this = id_cur;
+        if (more) {
+            st.issue((v + 1) & 1, recs, id_next);
+            id_cur = id_next;
+            id_next = (c >= 2) ? ids[(c - 2) * 32 + lane] : -1;
+        }
+        st.wait(v & 1, more);
+        const SplatRec* chunk = &s_rec[warp][v & 1][0];
+        const int nk = min(32, kmax - c * 32);
+        for (int kk = nk - 1; kk >= 0; kk--) {
+            const int k = c * 32 + kk;
+            const float4 q0 = *reinterpret_cast<const float4*>(&chunk[kk].px);   // px py A B
+            const float4 q1 = *reinterpret_cast<const float4*>(&chunk[kk].C);    // C o r g
+            const float cb = chunk[kk].b;
+            const float dx = q0.x - fx, dy0 = q0.y - fy0;
+            const float a2 = (-0.5f * LOG2E) * q0.z, b2 = (-LOG2E) * q0.w, c2 = (-0.5f * LOG2E) * q1.x;
+            const float base = a2 * dx * dx, lin = b2 * dx;
+            const float2 os2 = bc2(q1.y * KS), o2 = bc2(q1.y), c22 = bc2(c2), lin2 = bc2(lin), base2 = bc2(base);
+            const float2 cr2 = bc2(q1.z), cg2 = bc2(q1.w), cb2 = bc2(cb), dy02 = bc2(dy0);
+            float2 s0 = bc2(0.f), s1 = bc2(0.f), s2 = bc2(0.f), dr = bc2(0.f), dg = bc2(0.f), db = bc2(0.f);
+            float esq = 0.f, runx = 0.f, runy = 0.f;
+            bool any = false;
+#pragma unroll
+            for (int p = 0; p < NP; p++) {
+                const float2 dy = __fadd2_rn(dy02, make_float2(-(float)(2 * p), -(float)(2 * p + 1)));
+                const float2 pw = __ffma2_rn(dy, __ffma2_rn(c22, dy, lin2), base2);      // same two roundings as the forward's fmaf chain
+                float2 G = make_float2(fast_ex2(pw.x), fast_ex2(pw.y));
+                // contribution test = the forward's expression bit for bit (os * G >= A_MIN_S), and the pixel must still have
+                // been active at list position k
+                const float2 tt = __fmul2_rn(os2, G);
+                const bool ok0 = (tt.x >= A_MIN_S) && (k < nl[2 * p]);
+                const bool ok1 = (tt.y >= A_MIN_S) && (k < nl[2 * p + 1]);
+                any |= ok0 | ok1;
+                G.x = ok0 ? G.x : 0.0f;
+                G.y = ok1 ? G.y : 0.0f;
+                const float2 at = __fmul2_rn(o2, G);
+                const float2 a = make_float2(fminf(at.x, ALPHA_MAX), fminf(at.y, ALPHA_MAX));
+                const float2 om = __ffma2_rn(a, bc2(-1.0f), bc2(1.0f));                  // 1 - a
+                const float2 rc = make_float2(fast_rcp(om.x), fast_rcp(om.y));
+                float2 Tn = __fmul2_rn(T[p], rc);                                        // transmittance in front of this splat
+                Tn.x = fminf(1.0f, Tn.x); Tn.y = fminf(1.0f, Tn.y);
+                T[p] = Tn;
+                const float2 w = __fmul2_rn(a, Tn);
+                const float2 cgd = __ffma2_rn(cr2, g0[p], __ffma2_rn(cg2, g1[p], __fmul2_rn(cb2, g2[p])));
+                const float2 diff = __ffma2_rn(S[p], bc2(-1.0f), cgd);                   // (c - R) . g
+                float2 da = __fmul2_rn(Tn, diff);
+                if (TRANS) da = __ffma2_rn(ngt[p], rc, da);
+                S[p] = __ffma2_rn(a, diff, S[p]);
+                const float2 dpw = __fmul2_rn(at, da);      // passes through the 255/256 clamp (GR/raster.cu:776-778)
+                dr = __ffma2_rn(w, g0[p], dr); dg = __ffma2_rn(w, g1[p], dg); db = __ffma2_rn(w, g2[p], db);
+                s0 = __fadd2_rn(s0, dpw);
+                const float2 td = __fmul2_rn(dpw, dy);
+                s1 = __fadd2_rn(s1, td);
+                s2 = __ffma2_rn(td, dy, s2);
+                if (STAT) {
+                    const float2 go = __fmul2_rn(G, da);
+                    if (err_mode == 1) {
+                        if (__any_sync(FULL_MASK, ok0 | ok1)) {      // the reference skips a pair no lane of the warp reaches
+                            runx += go.x; runy += go.y;
+                            esq = fmaf(runx, runx, fmaf(runy, runy, esq));
+                        }
+                    } else {
+                        esq = fmaf(go.x, go.x, fmaf(go.y, go.y, esq));
+                    }
+                }
+            }
+            if (__any_sync(FULL_MASK, any)) {
+                // raw moments (LGS_GRAD_* slots, common.cuh): the conic factors are applied once per splat by the consumer
+                const float m0 = s0.x + s0.y, m1 = s1.x + s1.y, m2 = s2.x + s2.y;
+                const float u0 = dx * m0;
+                const int pid = __shfl_sync(FULL_MASK, id_this, kk);
+                float* row = &s_acc[warp][pend * NV][lane];
+                row[0 * LGS_ROWF] = u0;                    // sum dx s0
+                row[1 * LGS_ROWF] = m1;                    // sum s1
+                row[2 * LGS_ROWF] = dx * u0;               // sum dx^2 s0
+                row[3 * LGS_ROWF] = dx * m1;               // sum dx s1
+                row[4 * LGS_ROWF] = m2;                    // sum s2
+                row[5 * LGS_ROWF] = dr.x + dr.y;
+                row[6 * LGS_ROWF] = dg.x + dg.y;
+                row[7 * LGS_ROWF] = db.x + db.y;
+                row[8 * LGS_ROWF] = m0;                    // sum s0
+                if (STAT) row[9 * LGS_ROWF] = esq;
+                if (pend == 0) pid0 = pid; else if (pend == 1) pid1 = pid; else pid2 = pid;
+                pend++;
+                if (pend == LGS_RG) flush();
+            }
+        }
+        __syncwarp();
+    }
+    if (pend > 0) flush();
+    st.drain();
+}
+
 // ---- unpack ----------------------------------------------------------------------------------------
-// 12-float accumulator -> the reference's SoA gradient tensors (GR/raster.cu:855-886), including the
-// de-normaliser of the max-normalised image gradient (wrapper.py:490-494).
-__global__ void unpack_kernel(const float* __restrict__ grad, const float* __restrict__ inv_scaler, int N, int H, int W,
-                              float* __restrict__ d_ndc, float* __restrict__ d_cov, float* __restrict__ d_color,
+// 12-float raw-moment accumulator (LGS_GRAD_* slots, common.cuh) + the splat's record -> the reference's SoA gradient
+// tensors (GR/raster.cu:826-841 for the conic factors, :855-886 for the layout), including the de-normaliser of the
+// max-normalised image gradient (wrapper.py:490-494).
+__global__ void unpack_kernel(const float* __restrict__ grad, const SplatRec* __restrict__ recs, const float* __restrict__ inv_scaler,
+                              int N, int H, int W, float* __restrict__ d_ndc, float* __restrict__ d_cov, float* __restrict__ d_color,
                               float* __restrict__ d_opac, float* __restrict__ err_sum, float* __restrict__ err_sq)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
@@ -521,14 +742,62 @@ __global__ void unpack_kernel(const float* __restrict__ grad, const float* __res
     const float s = inv_scaler ? inv_scaler[0] : 1.0f;
     const float4* g4 = reinterpret_cast<const float4*>(grad + ((size_t)b * N + i) * LGS_GRAD_FLOATS);
     const float4 a = g4[0], c = g4[1], e = g4[2];
+    const SplatRec r = recs[(size_t)b * N + i];
+    LgsRasterGrad g;
+    lgs_finish_raster_grad(a, c, e, r.A, r.B, r.C, r.o, g);
     size_t o4 = (size_t)b * 4 * N + i, o3 = (size_t)b * 3 * N + i;
-    d_ndc[o4] = a.x * 0.5f * W * s; d_ndc[o4 + N] = a.y * 0.5f * H * s;
+    d_ndc[o4] = g.dmx * 0.5f * W * s; d_ndc[o4 + N] = g.dmy * 0.5f * H * s;
     d_ndc[o4 + 2 * (size_t)N] = 0.f; d_ndc[o4 + 3 * (size_t)N] = 0.f;
-    d_cov[o4] = a.z * s; d_cov[o4 + N] = a.w * 0.5f * s; d_cov[o4 + 2 * (size_t)N] = a.w * 0.5f * s; d_cov[o4 + 3 * (size_t)N] = c.x * s;
+    d_cov[o4] = g.dA * s; d_cov[o4 + N] = g.dB * 0.5f * s; d_cov[o4 + 2 * (size_t)N] = g.dB * 0.5f * s; d_cov[o4 + 3 * (size_t)N] = g.dC * s;
     d_color[o3] = c.y * s; d_color[o3 + N] = c.z * s; d_color[o3 + 2 * (size_t)N] = c.w * s;
-    if (b == 0) d_opac[i] = e.x * s;                      // view 0 only, as GR/raster.cu:881-884
+    if (b == 0) d_opac[i] = g.dop * s;                    // view 0 only, as GR/raster.cu:881-884
     if (err_sum) err_sum[(size_t)b * N + i] = 0.f;
     if (err_sq) err_sq[(size_t)b * N + i] = e.y;
+}
+
+// ---- tile order ------------------------------------------------------------------------------------
+// order[] = tile ids (1-based) by DESCENDING work (counting sort on work/4, 1024 buckets, one CTA per view), so that the
+// raster grid's CTAs -- dispatched in index order -- start the longest lists first and the last wave is made of short
+// ones (longest-processing-time-first; the reference orders its tiles by last epoch's blend count, render/__init__.py:75-79,
+// statistic_helper.py:68-79).  Order inside a bucket is unspecified.
+__global__ void __launch_bounds__(1024) tile_order_kernel(const int* __restrict__ work, int ntile, int* __restrict__ order)
+{
+    __shared__ int s_cnt[1024];
+    __shared__ int s_warp[32];
+    const int t = threadIdx.x, b = blockIdx.x;
+    const int* w = work + (size_t)b * ntile;
+    s_cnt[t] = 0;
+    __syncthreads();
+    for (int i = t; i < ntile; i += 1024) atomicAdd(&s_cnt[1023 - min(max(w[i], 0) >> 2, 1023)], 1);
+    __syncthreads();
+    // exclusive scan of the 1024 bucket counts
+    const int c = s_cnt[t];
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL_MASK, incl, o); if ((t & 31) >= o) incl += v; }
+    if ((t & 31) == 31) s_warp[t >> 5] = incl;
+    __syncthreads();
+    if (t < 32) {
+        int v = s_warp[t], in2 = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(FULL_MASK, in2, o); if (t >= o) in2 += u; }
+        s_warp[t] = in2 - v;
+    }
+    __syncthreads();
+    s_cnt[t] = incl - c + s_warp[t >> 5];
+    __syncthreads();
+    for (int i = t; i < ntile; i += 1024) {
+        const int pos = atomicAdd(&s_cnt[1023 - min(max(w[i], 0) >> 2, 1023)], 1);
+        order[(size_t)b * ntile + pos] = i + 1;
+    }
+}
+
+extern "C" int lgs_tile_order(const int* work, int V, int ntile, int* order, void* stream)
+{
+    LGS_REQUIRE(V >= 1 && ntile >= 1, "tile_order: bad sizes V=%d tiles=%d", V, ntile);
+    tile_order_kernel<<<V, 1024, 0, (cudaStream_t)stream>>>(work, ntile, order);
+    LGS_CHECK_LAUNCH("tile_order_kernel");
+    return LGS_OK;
 }
 
 // ---- host entry points -----------------------------------------------------------------------------
@@ -556,6 +825,34 @@ static bool use_deferred_reduce()
     return g_defer == 1;
 }
 extern "C" int lgs_set_backward_reduce(int deferred) { g_defer = deferred ? 1 : 0; return LGS_OK; }
+
+// backward kernel: 2 = packed-pair kernel (default), 1 = the scalar kernel (kept as A/B and for the TMA staging variant).
+// env LGS_BWD=v1|v2
+static int g_bwd = -1;
+static int backward_version()
+{
+    if (g_bwd < 0) {
+        const char* e = getenv("LGS_BWD");
+        g_bwd = (e && (e[0] == '1' || (e[0] == 'v' && e[1] == '1'))) ? 1 : 2;
+    }
+    return g_bwd;
+}
+extern "C" int lgs_set_backward_kernel(int version)
+{
+    LGS_REQUIRE(version == 1 || version == 2, "set_backward_kernel: %d not in {1,2}", version);
+    g_bwd = version;
+    return LGS_OK;
+}
+
+// densification error statistic (enable_statistic): 1 = the reference's lane-running recurrence (GR/raster.cu:779-784,
+// default), 0 = sum over pixels of (G dalpha)^2.  Only the packed-pair kernel implements mode 1.
+static int g_err_mode = 1;
+extern "C" int lgs_set_err_square_mode(int mode)
+{
+    LGS_REQUIRE(mode == 0 || mode == 1, "set_err_square_mode: %d not in {0,1}", mode);
+    g_err_mode = mode;
+    return LGS_OK;
+}
 
 // warps (= tiles) per CTA for the raster kernels: 1, 2 or 4.  Warps of a CTA are independent (no block-level
 // synchronisation), so this only trades CTA-retirement granularity against launch overhead.
@@ -593,7 +890,7 @@ extern "C" int lgs_rasterize_forward_packed(const int* sorted_points, const int*
                                             const int* specific_tiles, int n_specific, int V, int N, int cap, int img_h, int img_w,
                                             int tile_h, int tile_w, int enable_statistic, int clamp_zero, float* img,
                                             float* transmittance, short* last_contributor, int* fragment_count,
-                                            float* fragment_weight, void* stream)
+                                            float* fragment_weight, int* tile_work, void* stream)
 {
     LGS_REQUIRE(lgs_tile_ok(tile_h, tile_w), "rasterize_forward: tile %dx%d not one of 8x16, 12x16, 16x16, 8x8", tile_h, tile_w);
     LGS_REQUIRE(V >= 1 && img_h > 0 && img_w > 0, "rasterize_forward: bad sizes V=%d H=%d W=%d", V, img_h, img_w);
@@ -607,7 +904,7 @@ extern "C" int lgs_rasterize_forward_packed(const int* sorted_points, const int*
     const SplatRec* recs = (const SplatRec*)packed_params;
     const bool bulk = use_bulk();
 #define FWD(S, B) raster_forward_kernel<TH, TW, S, B><<<grid, block, 0, st>>>(sorted_points, start_index, recs, specific_tiles, n_specific, \
-        img, transmittance, last_contributor, fragment_count, fragment_weight, gx, ntile, cap, N, Hp, Wp, clamp_zero)
+        img, transmittance, (unsigned short*)last_contributor, fragment_count, fragment_weight, tile_work, gx, ntile, cap, N, Hp, Wp, clamp_zero)
     LGS_DISPATCH_TILE(tile_h, tile_w,
         if (enable_statistic) { if (bulk) FWD(true, true); else FWD(true, false); }
         else { if (bulk) FWD(false, true); else FWD(false, false); })
@@ -640,9 +937,19 @@ extern "C" int lgs_rasterize_backward(const int* sorted_points, const int* start
         const bool bulk = use_bulk();
         const bool trans = d_trans_img != nullptr;
         const bool defer = use_deferred_reduce() && !bulk;
+        const unsigned short* lastu = (const unsigned short*)last_contributor;
+        if (backward_version() == 2 && !bulk) {
+#define BW2(S, T) raster_backward_v2_kernel<TH, TW, S, T><<<grid, block, 0, st>>>(sorted_points, start_index, recs, specific_tiles, n_specific, \
+        final_transmittance, lastu, d_img, d_trans_img, clamped_img, packed_grad, gx, ntile, cap, N, Hp, Wp, g_err_mode)
+            LGS_DISPATCH_TILE(tile_h, tile_w,
+                if (enable_statistic) { if (trans) BW2(true, true); else BW2(true, false); }
+                else { if (trans) BW2(false, true); else BW2(false, false); })
+#undef BW2
+            LGS_CHECK_LAUNCH("raster_backward_v2_kernel");
+        } else {
 #define BWD(S, T, B) if (defer) BWD2(S, T, false, true); else BWD2(S, T, B, false)
 #define BWD2(S, T, B, D) raster_backward_kernel<TH, TW, S, T, B, D><<<grid, block, 0, st>>>(sorted_points, start_index, recs, specific_tiles, \
-        n_specific, final_transmittance, last_contributor, d_img, d_trans_img, clamped_img, packed_grad, gx, ntile, cap, N, Hp, Wp)
+        n_specific, final_transmittance, lastu, d_img, d_trans_img, clamped_img, packed_grad, gx, ntile, cap, N, Hp, Wp)
         LGS_DISPATCH_TILE(tile_h, tile_w,
             if (enable_statistic) { if (trans) { if (bulk) BWD(true, true, true); else BWD(true, true, false); }
                                     else { if (bulk) BWD(true, false, true); else BWD(true, false, false); } }
@@ -651,10 +958,11 @@ extern "C" int lgs_rasterize_backward(const int* sorted_points, const int* start
 #undef BWD
 #undef BWD2
         LGS_CHECK_LAUNCH("raster_backward_kernel");
+        }
     }
     if (d_ndc != nullptr) {
-        unpack_kernel<<<dim3(lgs_cdiv(N, 256), V), 256, 0, st>>>(packed_grad, grad_inv_scaler, N, img_h, img_w, d_ndc, d_cov2d_inv, d_color,
-                                                                d_opacity, err_sum, err_square_sum);
+        unpack_kernel<<<dim3(lgs_cdiv(N, 256), V), 256, 0, st>>>(packed_grad, (const SplatRec*)packed_params, grad_inv_scaler, N, img_h, img_w,
+                                                                d_ndc, d_cov2d_inv, d_color, d_opacity, err_sum, err_square_sum);
         LGS_CHECK_LAUNCH("unpack_kernel");
     }
     return LGS_OK;

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from typing import Optional
 
 import torch
@@ -26,6 +27,7 @@ _F32, _I32, _I64 = torch.float32, torch.int32, torch.int64
 CONFIG = {
     "fix_last_tile": True,          # close the last populated tile's range (reference leaves it empty)
     "true_sigmoid_grad": False,     # False = reference's d_o * sigma(x) on the cluster path
+    "tile_order": os.environ.get("LGS_TILE_ORDER", "1") != "0",   # fused pipeline: backward tiles launched heaviest-first (lgs_tile_order)
 }
 
 
@@ -394,7 +396,7 @@ def _raster_forward_impl(sorted_points, start_index, packed, specific_tiles, img
     fc = torch.zeros((V, 1, N), dtype=_I32, device=dev)
     fw = torch.zeros((V, 1, N), dtype=_F32, device=dev)
     _lib.call("lgs_rasterize_forward_packed", _ptr(sp), _ptr(si), _ptr(packed), _ptr(tiles), n_sel, V, N, cap, int(img_h), int(img_w),
-              int(th), int(tw), int(bool(enable_statistic)), 0, _ptr(img), _ptr(T), _ptr(last), _ptr(fc), _ptr(fw), _stream(dev))
+              int(th), int(tw), int(bool(enable_statistic)), 0, _ptr(img), _ptr(T), _ptr(last), _ptr(fc), _ptr(fw), None, _stream(dev))
     return img, T, depth, last, fc, fw
 
 

@@ -58,7 +58,8 @@ class ViewState:
     sorted_pid: torch.Tensor         # i32[1, D]
     ranges: torch.Tensor             # i32[1, tiles+2]
     T: torch.Tensor                  # f32[1,1,Hp,Wp]
-    last: torch.Tensor               # i16[1,1,Hp,Wp]
+    last: torch.Tensor               # i16[1,1,Hp,Wp] (unsigned 16-bit counts)
+    tile_order: Optional[torch.Tensor] = None   # i32[1,tiles]: tile ids, heaviest backward work first
 
 
 class _Pinned:
@@ -166,12 +167,18 @@ def render_view_forward(params: dict, cluster_origin: torch.Tensor, cluster_exte
             fc = torch.zeros((1, 1, Nmax), dtype=_I32, device=dev)
             fw = torch.zeros((1, 1, Nmax), dtype=_F32, device=dev)
             stats = (fc, fw)
+        # per-tile trip count of the backward (deepest list position any pixel consumed) -> heaviest-first tile order
+        order = None
+        work = torch.empty((1, ntile), dtype=_I32, device=dev) if (CONFIG["tile_order"] and specific_tiles is None and D > 0) else None
         _lib.call("lgs_rasterize_forward_packed", _ptr(sorted_pid), _ptr(ranges), _ptr(packed), _ptr(specific_tiles), n_sel, 1,
                   Nmax, sorted_pid.shape[1], H, W, th, tw, int(bool(enable_statistic)), int(bool(clamp_zero)), _ptr(img), _ptr(T),
-                  _ptr(last), _ptr(fc), _ptr(fw), st)
+                  _ptr(last), _ptr(fc), _ptr(fw), _ptr(work), st)
+        if work is not None:
+            order = torch.empty((1, ntile), dtype=_I32, device=dev)
+            _lib.call("lgs_tile_order", _ptr(work), 1, ntile, _ptr(order), st)
     state = ViewState(sh_degree=int(sh_degree), hw=(H, W), tile=(th, tw), n_chunks_visible=nvis, n_pairs=D, chunk_ids=ids,
                       counters=counters, view=view_matrix, proj=proj_matrix, packed=packed, tile_count=tcount,
-                      sorted_pid=sorted_pid, ranges=ranges, T=T, last=last)
+                      sorted_pid=sorted_pid, ranges=ranges, T=T, last=last, tile_order=order)
     return img, state, stats
 
 
@@ -201,6 +208,8 @@ def render_view_backward(params: dict, state: ViewState, d_img: torch.Tensor, d_
     with _on(dev):
         st = _stream(dev)
         pg = torch.empty((1, Nmax, 12), dtype=_F32, device=dev)
+        if specific_tiles is None:
+            specific_tiles = state.tile_order          # every tile, longest lists first (None = index order)
         n_sel = 0 if specific_tiles is None else specific_tiles.shape[1]
         _lib.call("lgs_rasterize_backward", _ptr(state.sorted_pid), _ptr(state.ranges), _ptr(state.packed), _ptr(specific_tiles), n_sel,
                   _ptr(state.T), _ptr(state.last), _ptr(d_img), _ptr(d_trans), _ptr(clamped_img), None, 1, Nmax, state.sorted_pid.shape[1],

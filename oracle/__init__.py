@@ -298,8 +298,11 @@ def rasterize_forward(sorted_points, start_index, ndc, cov2d_inv, color, opacity
 
 def rasterize_backward(sorted_points, start_index, ndc, cov2d_inv, color, opacity, specific_tiles,
                        final_T, last_contributor, d_img, d_trans, grad_inv_scaler,
-                       img_h, img_w, tile_h, tile_w, enable_statistic=False):
-    """GR/raster.cu:917-1037 -> (d_ndc [V,4,N], d_cov2d_inv [V,2,2,N], d_color [V,3,N], d_opacity [1,N], err_sum, err_sq)."""
+                       img_h, img_w, tile_h, tile_w, enable_statistic=False, err_mode="reference"):
+    """GR/raster.cu:917-1037 -> (d_ndc [V,4,N], d_cov2d_inv [V,2,2,N], d_color [V,3,N], d_opacity [1,N], err_sum, err_sq).
+
+    err_mode: "reference" = the lane-running recurrence of GR/raster.cu:779-784 (orc_raster_err_square_ref),
+    "pixel" = sum over pixels of (G dalpha)^2."""
     dt = ndc.dtype; V = ndc.shape[0]; N = ndc.shape[2]
     sp = _c(sorted_points, np.int32); cap = sp.shape[1]
     d_ndc = np.zeros((V, 4, N), dt); d_cov = np.zeros((V, 2, 2, N), dt); d_col = np.zeros((V, 3, N), dt)
@@ -311,6 +314,11 @@ def rasterize_backward(sorted_points, start_index, ndc, cov2d_inv, color, opacit
           _c(last_contributor, np.int16), _c(d_img, dt), None if d_trans is None else _c(d_trans, dt), scaler,
           V, N, cap, int(img_h), int(img_w), int(tile_h), int(tile_w), d_ndc, d_cov, d_col, d_op,
           err if enable_statistic else None)
+    if enable_statistic and err_mode == "reference":
+        _call("orc_raster_err_square_ref", dt, sp, _c(start_index, np.int32), _c(ndc), _c(cov2d_inv, dt), _c(color, dt),
+              _c(opacity, dt), tiles, 0 if tiles is None else tiles.shape[1], _c(final_T, dt),
+              _c(last_contributor, np.int16), _c(d_img, dt), None if d_trans is None else _c(d_trans, dt),
+              V, N, cap, int(img_h), int(img_w), int(tile_h), int(tile_w), err)
     return d_ndc, d_cov, d_col, d_op, np.zeros((V, 1, N), dt), err
 
 

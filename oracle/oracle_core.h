@@ -751,7 +751,7 @@ void SUF(orc_raster_forward)(const int32_t* sorted, const int32_t* range, const 
                 img[((size_t)b * 3 + 1) * plane + po] = FMIN(C1, (REAL)1.0);
                 img[((size_t)b * 3 + 2) * plane + po] = FMIN(C2, (REAL)1.0);
                 Tout[(size_t)b * plane + po] = T;
-                last[(size_t)b * plane + po] = (int16_t)n;
+                last[(size_t)b * plane + po] = (int16_t)(uint16_t)(n > 65535 ? 65535 : n);   /* 16-bit count, read back unsigned (GR/raster.cu:683-686) */
                 if (fragile) fragile[(size_t)b * plane + po] = (uint8_t)frag;
             }
         }
@@ -793,7 +793,7 @@ void SUF(orc_raster_backward)(const int32_t* sorted, const int32_t* range, const
                      g2 = d_img[((size_t)b * 3 + 2) * plane + po];
                 REAL gT = d_trans ? d_trans[(size_t)b * plane + po] : 0;
                 REAL R0 = 0, R1 = 0, R2 = 0;
-                int n = last[(size_t)b * plane + po];
+                int n = (int)(uint16_t)last[(size_t)b * plane + po];
                 for (int k = n - 1; k >= 0; k--) {
                     int i = sorted[(size_t)b * cap + start + k];
                     SUF(splat_rec) s = SUF(load_rec)(ndc, inv_cov, color, opac, b, N, i, H, W);
@@ -852,6 +852,96 @@ void SUF(orc_raster_backward)(const int32_t* sorted, const int32_t* range, const
         if (err_sq) err_sq[(size_t)b * N + i] = (REAL)acc_err[(size_t)b * N + i];
     }
     free(acc); if (acc_err) free(acc_err);
+}
+
+/* err_square_sum exactly as the reference accumulates it (GR/raster.cu:744-784,812-820): one warp owns a tile, lane l owns
+ * the column strip x = l % TW, rows (l / TW) * PPT .. + PPT - 1 with PPT = TH*TW/32 (:644-645), handled as PPT/2 vertical
+ * PAIRS (rows 2i, 2i+1).  Per splat the lane keeps a running sum of G*dalpha over its even rows and one over its odd rows;
+ * after every pair that ANY lane of the warp reaches (:758) the two running sums are squared and added (:779-784), and the
+ * lanes' totals are summed into err_square_sum (:812-818) when any lane has a non-zero d_opacity (:796).  This is NOT the
+ * sum over pixels of (G dalpha)^2: it depends on the lane layout, which is part of the reference's contract for the
+ * densification score (densify.py:286-292).  Same inputs as orc_raster_backward; err_sq [V,1,N] is overwritten. */
+void SUF(orc_raster_err_square_ref)(const int32_t* sorted, const int32_t* range, const REAL* ndc, const REAL* inv_cov,
+                                   const REAL* color, const REAL* opac, const int32_t* tiles, int ntiles_sel,
+                                   const REAL* Tfinal, const int16_t* last, const REAL* d_img, const REAL* d_trans,
+                                   int V, int N, int cap, int H, int W, int TH, int TW, REAL* err_sq)
+{
+    int gx = (W + TW - 1) / TW, gy = (H + TH - 1) / TH;
+    int Hp = gy * TH, Wp = gx * TW, ntile = gx * gy;
+    int nrender = tiles ? ntiles_sel : ntile;
+    int PPT = TH * TW / 32, NPAIR = PPT / 2, npx = TH * TW;
+    size_t plane = (size_t)Hp * Wp;
+    double* acc = (double*)calloc((size_t)V * N, sizeof(double));
+    for (int b = 0; b < V; b++) {
+        const int32_t* rg = range + (size_t)b * (ntile + 2);
+#pragma omp parallel for schedule(dynamic, 4)
+        for (int ti = 0; ti < nrender; ti++) {
+            int tid = tiles ? tiles[(size_t)b * ntiles_sel + ti] : ti + 1;
+            if (tid == 0 || tid >= ntile + 1) continue;
+            int start = rg[tid];
+            if (start == -1) continue;
+            int tx = (tid - 1) % gx, ty = (tid - 1) / gx;
+            /* per-pixel state of the back-to-front walk, pixel index = lane * PPT + j */
+            REAL* T = (REAL*)malloc(sizeof(REAL) * npx * 6);
+            REAL* R0 = T + npx; REAL* R1 = R0 + npx; REAL* R2 = R1 + npx; REAL* go = R2 + npx; REAL* Tf = go + npx;
+            int* nn = (int*)malloc(sizeof(int) * npx);
+            unsigned char* ok = (unsigned char*)malloc(npx);
+            int kmax = 0;
+            for (int l = 0; l < 32; l++) for (int j = 0; j < PPT; j++) {
+                int x = tx * TW + l % TW, y = ty * TH + (l / TW) * PPT + j;
+                size_t po = (size_t)y * Wp + x;
+                int q = l * PPT + j;
+                T[q] = Tfinal[(size_t)b * plane + po]; Tf[q] = T[q];
+                R0[q] = R1[q] = R2[q] = 0;
+                nn[q] = (int)(uint16_t)last[(size_t)b * plane + po];
+                if (nn[q] > kmax) kmax = nn[q];
+            }
+            for (int k = kmax - 1; k >= 0; k--) {
+                int i = sorted[(size_t)b * cap + start + k];
+                SUF(splat_rec) s = SUF(load_rec)(ndc, inv_cov, color, opac, b, N, i, H, W);
+                int any_nonzero = 0;
+                for (int l = 0; l < 32; l++) for (int j = 0; j < PPT; j++) {
+                    int x = tx * TW + l % TW, y = ty * TH + (l / TW) * PPT + j;
+                    size_t po = (size_t)y * Wp + x;
+                    int q = l * PPT + j;
+                    ok[q] = 0; go[q] = 0;
+                    if (k >= nn[q]) continue;
+                    REAL dx = s.px - x, dy = s.py - y;
+                    REAL pw = (REAL)-0.5 * (s.A * dx * dx + 2 * s.B * dx * dy + s.C * dy * dy);
+                    REAL G = EXP(pw);
+                    REAL a = s.o * G;
+                    if (a < (REAL)1.0 / 256) continue;
+                    a = FMIN(a, (REAL)255.0 / 256);
+                    T[q] = FMIN((REAL)1.0, T[q] / (1 - a));
+                    REAL g0 = d_img[((size_t)b * 3 + 0) * plane + po], g1 = d_img[((size_t)b * 3 + 1) * plane + po],
+                         g2 = d_img[((size_t)b * 3 + 2) * plane + po];
+                    REAL da = T[q] * ((s.r - R0[q]) * g0 + (s.g - R1[q]) * g1 + (s.b - R2[q]) * g2);
+                    if (d_trans) da -= d_trans[(size_t)b * plane + po] * Tf[q] / (1 - a);
+                    R0[q] += a * (s.r - R0[q]); R1[q] += a * (s.g - R1[q]); R2[q] += a * (s.b - R2[q]);
+                    ok[q] = 1; go[q] = G * da;
+                    if (go[q] != 0) any_nonzero = 1;
+                }
+                if (!any_nonzero) continue;
+                double e = 0;
+                /* which pairs does the warp execute? (any lane valid in rows 2i, 2i+1) */
+                for (int l = 0; l < 32; l++) {
+                    double runx = 0, runy = 0;
+                    for (int pi = 0; pi < NPAIR; pi++) {
+                        int exec = 0;
+                        for (int l2 = 0; l2 < 32 && !exec; l2++) exec = ok[l2 * PPT + 2 * pi] | ok[l2 * PPT + 2 * pi + 1];
+                        if (!exec) continue;
+                        runx += go[l * PPT + 2 * pi]; runy += go[l * PPT + 2 * pi + 1];
+                        e += runx * runx + runy * runy;
+                    }
+                }
+#pragma omp atomic
+                acc[(size_t)b * N + i] += e;
+            }
+            free(T); free(nn); free(ok);
+        }
+    }
+    for (size_t q = 0; q < (size_t)V * N; q++) err_sq[q] = (REAL)acc[q];
+    free(acc);
 }
 
 /* ---- optimiser / statistics (next rows) --------------------------------------- */

@@ -103,6 +103,71 @@ def test_c2_level_a_equals_level_b(cuda):
         assert float((a - b).abs().max()) / (float(a.abs().max()) + 1e-30) < 2e-4, k
 
 
+def test_c2_one_view_matches_oracle(cuda):
+    """BASELINE.json configs[1] (the configuration the headline number is quoted on): ONE full-size view -- 1M Gaussians,
+    1920x1080, sh_degree 3, 8x16 tiles -- fused pipeline vs the CPU oracle: identical tile lists, image within 1e-4 and the six
+    parameter gradients within 2e-4 (pixels on a step-function threshold get zero loss weight)."""
+    import oracle
+    H, W, tile, deg = 1080, 1920, (8, 16), 3
+    p = scene.make_scene(1_000_000, sh_degree=3, seed=0)
+    params = {k: p[k] for k in KEYS}
+    aabb = (p["cluster_origin"], p["cluster_extend"])
+    cam = scene.make_camera(0, 64, W, H)
+    rng = np.random.default_rng(7)
+    w = rng.normal(size=(1, 3, H, W)).astype(np.float32)
+    o0 = oracle.render_forward_backward(params, aabb, cam, (H, W), tile, deg, lambda img: w)
+    frag = o0["fragile"][:, :H, :W]
+    assert frag.mean() < 0.10          # ~700 listed splats per pixel: 4-5 % of the pixels pass within 1e-5 of a threshold somewhere
+    w = w * (~frag)[:, None]
+    ref = oracle.render_forward_backward(params, aabb, cam, (H, W), tile, deg, lambda img: w)
+    P = {k: torch.from_numpy(params[k]).to(cuda).requires_grad_(True) for k in KEYS}
+    A = [torch.from_numpy(a).to(cuda) for a in aabb]
+    C = {k: torch.from_numpy(v).to(cuda) for k, v in cam.items()}
+    # per-tile lists first (integer work: bit-exact)
+    with torch.no_grad():
+        _, st, _ = pipeline.render_view_forward({k: P[k].detach() for k in KEYS}, A[0], A[1], C["frustumplane"], C["view"], C["proj"], deg,
+                                                (H, W), tile)
+    assert st.n_pairs == ref["sorted_pid"].shape[1]
+    assert np.array_equal(st.ranges.cpu().numpy(), ref["ranges"])
+    assert np.array_equal(st.sorted_pid.cpu().numpy(), ref["sorted_pid"])
+    lc = st.last.cpu().numpy()[:, 0, :H, :W].astype(np.uint16)
+    assert np.array_equal(lc[~frag], ref["last"][:, 0, :H, :W].astype(np.uint16)[~frag])
+    pp = PipelineParams(tile_size=tile)
+    img = render.render_view(A[0], A[1], C["frustumplane"], C["view"], C["proj"], P["xyz"], P["scale"], P["rot"], P["sh_0"], P["sh_rest"],
+                             P["opacity"], deg, (H, W), pp)[0]
+    (img * torch.from_numpy(w).to(cuda)).sum().backward()
+    ok = ~np.broadcast_to(frag[:, None], ref["img"].shape)
+    err = np.abs(img.detach().cpu().numpy()[ok] - ref["img"][ok]).max()
+    assert err < 1e-4, err
+    nvis = int(ref["visible_chunk_id"].shape[0])
+    for k in KEYS:
+        g = P[k].grad.compacted_values.cpu().numpy()[..., :nvis, :].astype(np.float64)
+        r = ref["grads"][k][..., :nvis, :].astype(np.float64)
+        e = float(np.abs(g - r).max() / np.abs(r).max())
+        assert e < 2e-4, (k, e)
+
+
+def test_c4_crop_tile_lists_match_oracle(cuda):
+    """BASELINE.json configs[3] scale on a crop the oracle can afford: the C4 recipe (log-scales shifted by -0.5, 16x16 tiles,
+    32-bit-free 16-bit tile keys at this size) on 400k Gaussians at 1920x1088 -- per-tile lists identical to the oracle's."""
+    import oracle
+    from tests.util import oracle_projected
+    H, W, tile = 1088, 1920, (16, 16)
+    lo, hi = 0.002 * np.exp(-0.5), 0.02 * np.exp(-0.5)
+    p = scene.make_scene(400_000, sh_degree=3, seed=3, log_scale_range=(lo, hi))
+    params = {k: p[k] for k in KEYS}
+    aabb = (p["cluster_origin"], p["cluster_extend"])
+    cam = scene.make_camera(9, 64, W, H)
+    o = oracle_projected(params, aabb, cam, (H, W), 3)
+    ranges, pid, _, _ = oracle.binning(o["ndc"], o["view_pos"][:, 2], o["inv_cov2d"], o["opacity"], None, (H, W), tile)
+    P = {k: torch.from_numpy(params[k]).to(cuda) for k in KEYS}
+    A = [torch.from_numpy(a).to(cuda) for a in aabb]
+    C = {k: torch.from_numpy(v).to(cuda) for k, v in cam.items()}
+    _, st, _ = pipeline.render_view_forward(P, A[0], A[1], C["frustumplane"], C["view"], C["proj"], 3, (H, W), tile)
+    assert st.n_pairs == pid.shape[1]
+    assert np.array_equal(st.ranges.cpu().numpy(), ranges) and np.array_equal(st.sorted_pid.cpu().numpy(), pid)
+
+
 def test_c4_5m_4k_stress(cuda):
     """5M Gaussians at 3840x2160: 32,400 16x16 tiles, tens of millions of pairs; int16 contributor counts must not
     overflow and the tile lists must stay consistent."""
@@ -114,7 +179,7 @@ def test_c4_5m_4k_stress(cuda):
     img, st, _ = pipeline.render_view_forward(P, A[0], A[1], cam["frustumplane"], cam["view"], cam["proj"], 3, (H, W), (16, 16))
     assert st.n_pairs > 10_000_000
     _list_properties(st, S)
-    assert int(st.last.min()) >= 0 and int(st.last.max()) < 32767
+    assert int(st.last.view(torch.uint16).to(torch.int32).max()) < 65535
     assert float(img.max()) <= 1.0 and bool(torch.isfinite(img).all())
     grads, _ = pipeline.render_view_backward(P, st, torch.ones_like(img))
     assert all(bool(torch.isfinite(g).all()) for g in grads)

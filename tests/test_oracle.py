@@ -179,3 +179,28 @@ def test_scene_conventions():
     p = scene.make_scene(1000, sh_degree=0)
     vis, num, ids = oracle.frustum_culling_aabb(p["cluster_origin"], p["cluster_extend"], cam["frustumplane"])
     assert num[0] == p["cluster_origin"].shape[1]                   # the unit cube is inside the frustum at distance 3
+
+
+def test_err_square_reference_recurrence_properties():
+    """orc_raster_err_square_ref (GR/raster.cu:779-784): with 8x8 tiles a lane owns ONE pixel pair, so the lane-running
+    recurrence degenerates to the per-pixel sum of squares; with more pairs per lane it is larger or equal wherever the
+    running sums keep their sign, and it never is negative."""
+    import oracle
+    from tests.util import oracle_projected, small_scene
+    hw = (64, 96)
+    params, aabb, cam = small_scene(n=1500, hw=hw)
+    o = oracle_projected(params, aabb, cam, hw, 3)
+    rng = np.random.default_rng(0)
+    for tile in ((8, 8), (8, 16), (16, 16)):
+        th, tw = tile
+        ranges, pid, _, _ = oracle.binning(o["ndc"], o["view_pos"][:, 2], o["inv_cov2d"], o["opacity"], None, hw, tile)
+        img, T, last, _, _, _ = oracle.rasterize_forward(pid, ranges, o["ndc"], o["inv_cov2d"], o["color"], o["opacity"], None, hw[0], hw[1], th, tw)
+        g = rng.normal(size=img.shape).astype(np.float32)
+        args = (pid, ranges, o["ndc"], o["inv_cov2d"], o["color"], o["opacity"], None, T, last, g, None, 1.0, hw[0], hw[1], th, tw)
+        e_ref = oracle.rasterize_backward(*args, enable_statistic=True, err_mode="reference")[5]
+        e_pix = oracle.rasterize_backward(*args, enable_statistic=True, err_mode="pixel")[5]
+        assert e_ref.min() >= 0 and e_pix.max() > 0
+        if tile == (8, 8):
+            assert np.abs(e_ref - e_pix).max() <= 1e-5 * e_pix.max()
+        else:
+            assert np.abs(e_ref - e_pix).max() > 1e-3 * e_pix.max()      # a different statistic, not a rounding variant
