@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--level", default="B", choices=["A", "B"], help="B = fused render_view (default), A = op-by-op surface")
     ap.add_argument("--staging", default=None, choices=[None, "bulk", "cpasync"])
-    ap.add_argument("--streams", type=int, default=3, help="CUDA streams the views of a step alternate over (1 = serial)")
+    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the views of a step alternate over (1 = serial)")
     return ap.parse_args()
 
 

@@ -193,7 +193,7 @@ def _streams(dev, n):
 
 def render_views(n_views: int, camera_fn, loss_fn, cluster_origin, cluster_extend,
                  xyz, scale, rot, sh_0, sh_rest, opacity, actived_sh_degree: int, output_shape, pp,
-                 accumulate_into: dict, n_streams: int = 3, loss_and_grad_fn=None):
+                 accumulate_into: dict, n_streams: int = 4, loss_and_grad_fn=None):
     """Forward + backward of a batch of views with the gradients summed into ``accumulate_into`` (dense tensors shaped
     like the parameters, e.g. ``GradAccumulator.grads()``).  This is the per-rank body of a data-parallel step.
 

@@ -95,6 +95,52 @@ def build_ssim(quiet: bool = False):
     return so_path(SSIM_NAME)
 
 
+REF_ROOT = "/root/reference"
+PY_OUT = os.path.join(os.path.dirname(HERE), "baseline", "_ref")
+
+
+def stage_python(quiet: bool = False):
+    """Stage the UNMODIFIED reference Python package (``litegs/`` without its native submodules, plus the example scripts)
+    under ``baseline/_ref`` (the location the bench contract reserves for an unmodified reference install) -- git-ignored,
+    NOT gpurun-ignored -- so that the drop-in test
+    (tests/test_gpu_dropin.py) and the ``ref_cuda`` bench leg can import the reference's own ``wrapper.py`` /
+    ``render/__init__.py`` / ``training/trainer.py`` on the GPU box, where /root/reference does not exist.  Files are byte
+    copies (checked by the test against a manifest of SHA-256 digests written here); nothing is copied into tracked paths."""
+    import hashlib
+    import json
+    import shutil
+    if not os.path.isdir(os.path.join(REF_ROOT, "litegs")):
+        if not quiet:
+            print("[build_ref] /root/reference not present: nothing to stage")
+        return PY_OUT if os.path.isdir(PY_OUT) else None
+    os.makedirs(PY_OUT, exist_ok=True)
+    manifest = {}
+    for top in ("litegs", "example_train.py", "example_metrics.py"):
+        src = os.path.join(REF_ROOT, top)
+        if os.path.isfile(src):
+            shutil.copy2(src, os.path.join(PY_OUT, top))
+            manifest[top] = hashlib.sha256(open(src, "rb").read()).hexdigest()
+            continue
+        for d, dirs, files in os.walk(src):
+            dirs[:] = [x for x in dirs if x not in ("submodules", "__pycache__")]
+            rel = os.path.relpath(d, REF_ROOT)
+            os.makedirs(os.path.join(PY_OUT, rel), exist_ok=True)
+            for f in files:
+                if f.endswith(".py"):
+                    shutil.copy2(os.path.join(d, f), os.path.join(PY_OUT, rel, f))
+                    manifest[os.path.join(rel, f)] = hashlib.sha256(open(os.path.join(d, f), "rb").read()).hexdigest()
+    json.dump(manifest, open(os.path.join(PY_OUT, "MANIFEST.json"), "w"), indent=1, sort_keys=True)
+    return PY_OUT
+
+
+def reference_python_path():
+    """Directory to put on sys.path to import the reference's ``litegs`` package: the mounted tree if present, else the
+    staged copy, else None."""
+    if os.path.isdir(os.path.join(REF_ROOT, "litegs")):
+        return REF_ROOT
+    return PY_OUT if os.path.isdir(os.path.join(PY_OUT, "litegs")) else None
+
+
 def _load(name: str):
     p = so_path(name)
     if p is None:
@@ -120,3 +166,4 @@ def load_ssim():
 if __name__ == "__main__":
     print(build(quiet="-q" in sys.argv))
     print(build_ssim(quiet="-q" in sys.argv))
+    print(stage_python(quiet="-q" in sys.argv))

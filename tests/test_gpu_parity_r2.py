@@ -64,7 +64,9 @@ def test_sh2rgb_autograd_wrapper_matches_fd(cuda):
     w = rng.normal(size=(1, 3, N)).astype(np.float32)
     rgb = wrapper.SphericalHarmonicToRGB.call_fused(3, sh0, shr, T(d, cuda))
     (rgb * T(w, cuda)).sum().backward()
-    o0, orr, _ = oracle.sh2rgb_backward(3, w, 15, d)
+    raw = oracle.sh2rgb_forward(3, sh0.detach().cpu().numpy(), shr.detach().cpu().numpy(), d)
+    assert (raw < 0).any() and float(rgb.min()) == 0.0            # the wrapper clamps at 0 (wrapper.py:558) ...
+    o0, orr, _ = oracle.sh2rgb_backward(3, w * (raw > 0), 15, d)  # ... and the clamp blocks the gradient there
     assert scaled_err(sh0.grad.cpu().numpy(), o0) < TOL and scaled_err(shr.grad.cpu().numpy(), orr) < TOL
 
 
@@ -142,21 +144,22 @@ def test_eigenvectors(cuda, proj):
     val, vec, inv = fused.eigh_and_inv_2x2matrix_forward(T(cov, cuda), None)
     oval, ovec, oinv = oracle.eigh_and_inv_2x2matrix_forward(cov)
     val, vec = val.cpu().numpy().astype(np.float64), vec.cpu().numpy().astype(np.float64)
-    # the same vectors as the oracle, up to the sign ambiguity of an eigenvector
-    s = np.sign((vec * ovec).sum(axis=2, keepdims=True))
+    # vec[b, i, k, n] = component i of eigenvector k (columns are the vectors, as torch.linalg.eigh: GR/transform.cu:1411-1412).
+    # The same vectors as the oracle, up to the sign ambiguity of an eigenvector
+    s = np.sign((vec * ovec).sum(axis=1, keepdims=True))
     s[s == 0] = 1
     close = np.abs(vec * s - ovec).max(axis=(1, 2))
     gap = np.abs(oval[:, 0] - oval[:, 1]) / np.maximum(np.abs(oval).max(axis=1), 1e-30)
     assert (close[gap > 1e-3] < 5e-4).all()                  # well separated eigenvalues: vectors agree
-    # and they ARE eigenvectors: cov v_k = lambda_k v_k, unit length, orthogonal  (row k of vec = k-th vector)
+    # and they ARE eigenvectors: cov v_k = lambda_k v_k, unit length, orthogonal
     c = cov.astype(np.float64)
     for k in range(2):
-        v = vec[:, k]                                        # [V,2,N]
+        v = vec[:, :, k]                                     # [V,2,N]
         cv = np.stack([c[:, 0, 0] * v[:, 0] + c[:, 0, 1] * v[:, 1], c[:, 1, 0] * v[:, 0] + c[:, 1, 1] * v[:, 1]], axis=1)
         res = np.abs(cv - val[:, k][:, None] * v).max(axis=1) / np.maximum(np.abs(val).max(axis=1), 1e-30)
         assert res.max() < 2e-4, res.max()
         assert np.abs((v * v).sum(axis=1) - 1).max() < 1e-4
-    assert np.abs((vec[:, 0] * vec[:, 1]).sum(axis=1)).max() < 1e-4
+    assert np.abs((vec[:, :, 0] * vec[:, :, 1]).sum(axis=1)).max() < 1e-4
 
 
 # ---------------------------------------------------------------------------------------------------
