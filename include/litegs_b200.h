@@ -156,6 +156,30 @@ int lgs_scan_gathered_workspace_bytes(int n, size_t* bytes);
 int lgs_scan_gathered(const int* counts, const unsigned* order, int n, int* out, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* ---- GPU-driven sizing: the same building blocks with the live counts read ON THE DEVICE -------------------------------
+ * `capacity` bounds the launch geometry and the buffers; the live count comes from a device int (clamped to the capacity), the
+ * depth-key bias from a device word.  Nothing is read back, so a whole view can be enqueued -- or captured in a CUDA graph --
+ * without a host synchronisation.  The reference gets the same effect by sizing from LAST epoch's counts through pinned
+ * feedback buffers (GR/compact.cu:527-549, GR/binning.cu:137-163, data.py:238); here the capacity is the caller's prediction
+ * and lgs_view_params raises a device-side flag when it was too small. */
+int lgs_view_params(const int* counters /* i32[4]: visible chunks, pairs, ~min depth key, max depth key */, int S, int pair_capacity,
+                    int planned_depth_bits, int* params /* i32[8], see csrc/fused.cu */, void* stream);
+int lgs_sort_pairs_u32_dev(const unsigned* keys_in, unsigned* keys_out, const unsigned* vals_in, unsigned* vals_out, int capacity,
+                           const int* n_dev, const unsigned* bias_dev, int end_bit, void* workspace, size_t workspace_bytes, void* stream);
+int lgs_sort_pairs_u16_dev(const unsigned short* keys_in, unsigned short* keys_out, const unsigned* vals_in, unsigned* vals_out,
+                           int capacity, const int* n_dev, int begin_bit, int end_bit, void* workspace, size_t workspace_bytes,
+                           void* stream);
+int lgs_sort_pairs_u32k_dev(const unsigned* keys_in, unsigned* keys_out, const unsigned* vals_in, unsigned* vals_out, int capacity,
+                            const int* n_dev, int begin_bit, int end_bit, void* workspace, size_t workspace_bytes, void* stream);
+int lgs_scan_gathered_dev(const int* counts, const unsigned* order, int capacity, const int* n_dev, int* out, void* workspace,
+                          size_t workspace_bytes, void* stream);
+int lgs_emit_pairs_dev(const float* packed_params, const int* offset, const unsigned* order, int n_capacity, const int* n_dev, int cap,
+                       int img_h, int img_w, int tile_h, int tile_w, int key_bits /* 16 | 32 */, void* keys, int* vals, void* stream);
+int lgs_tile_range_u16_dev(const unsigned short* table_tile_id, int capacity, const int* length_dev, int max_tile_id, int fix_last,
+                           int* tile_range, void* stream);
+int lgs_tile_range_dev(const int* table_tile_id, int capacity, const int* length_dev, int max_tile_id, int fix_last, int* tile_range,
+                       void* stream);
+
 /* ---- rasterisation ------------------------------------------------------------------------------------- */
 
 /* pack_forward_params, GR/raster.cu:334-356 -> packed f32[V,N,12] (fp32 record, see LGS_REC_FLOATS). */

@@ -198,8 +198,9 @@ __global__ void __launch_bounds__(256) tile_range_kernel(const KeyT* __restrict_
 //   anything else                    -> -1
 template <typename KeyT>
 __global__ void __launch_bounds__(256) tile_range_bsearch_kernel(const KeyT* __restrict__ keys, int L, int max_tile, int fix_last,
-                                                                 int* __restrict__ range)
+                                                                 int* __restrict__ range, const int* __restrict__ L_dev)
 {
+    if (L_dev != nullptr) L = min(L, max(*L_dev, 0));         // GPU-driven sizing: L is the capacity, *L_dev the live length
     // one WARP per tile: a 32-ary search (each lane probes the last key of one of 32 segments, a ballot counts the segments
     // that lie entirely below t) needs 5 rounds of independent loads at 1080p where a binary search needs 24 dependent ones
     const int lane = threadIdx.x & 31;
@@ -227,8 +228,15 @@ __global__ void __launch_bounds__(256) tile_range_bsearch_kernel(const KeyT* __r
 }
 
 template <typename KeyT>
-static int tile_range_launch(const KeyT* keys, int V, int L, int max_tile, int fix_last, int* range, cudaStream_t st)
+static int tile_range_launch(const KeyT* keys, int V, int L, int max_tile, int fix_last, int* range, cudaStream_t st,
+                             const int* L_dev = nullptr)
 {
+    if (L_dev != nullptr) {
+        LGS_REQUIRE(V == 1, "tile_range: the device-side length form handles one view per call");
+        tile_range_bsearch_kernel<KeyT><<<dim3(lgs_cdiv(max_tile + 2, 8), V), 256, 0, st>>>(keys, L, max_tile, fix_last, range, L_dev);
+        LGS_CHECK_LAUNCH("tile_range_bsearch_kernel");
+        return LGS_OK;
+    }
     if (L <= 0) {
         size_t n = (size_t)V * (max_tile + 2);
         fill_int_kernel<<<lgs_cdiv((long long)n, 256), 256, 0, st>>>(range, -1, n);
@@ -249,7 +257,7 @@ static int tile_range_launch(const KeyT* keys, int V, int L, int max_tile, int f
         LGS_CHECK_LAUNCH("tile_range_kernel");
         return LGS_OK;
     }
-    tile_range_bsearch_kernel<KeyT><<<dim3(lgs_cdiv(max_tile + 2, 8), V), 256, 0, st>>>(keys, L, max_tile, fix_last, range);
+    tile_range_bsearch_kernel<KeyT><<<dim3(lgs_cdiv(max_tile + 2, 8), V), 256, 0, st>>>(keys, L, max_tile, fix_last, range, nullptr);
     LGS_CHECK_LAUNCH("tile_range_bsearch_kernel");
     return LGS_OK;
 }
@@ -269,19 +277,40 @@ extern "C" int lgs_tile_range_u16(const unsigned short* table_tile_id, int V, in
     return tile_range_launch<unsigned short>(table_tile_id, V, table_length, max_tile_id, fix_last, tile_range, (cudaStream_t)stream);
 }
 
+// device-side length forms (GPU-driven sizing: `capacity` bounds the launch, *length_dev is the live length)
+extern "C" int lgs_tile_range_u16_dev(const unsigned short* table_tile_id, int capacity, const int* length_dev, int max_tile_id,
+                                      int fix_last, int* tile_range, void* stream)
+{
+    LGS_REQUIRE(capacity >= 0 && length_dev != nullptr && max_tile_id >= 0 && max_tile_id < 65535, "tileRange(u16,dev): bad arguments");
+    return tile_range_launch<unsigned short>(table_tile_id, 1, capacity, max_tile_id, fix_last, tile_range, (cudaStream_t)stream, length_dev);
+}
+
+extern "C" int lgs_tile_range_dev(const int* table_tile_id, int capacity, const int* length_dev, int max_tile_id, int fix_last,
+                                  int* tile_range, void* stream)
+{
+    LGS_REQUIRE(capacity >= 0 && length_dev != nullptr && max_tile_id >= 0, "tileRange(dev): bad arguments");
+    return tile_range_launch<int>(table_tile_id, 1, capacity, max_tile_id, fix_last, tile_range, (cudaStream_t)stream, length_dev);
+}
+
 // ------------------------------------------------------------------------------------------------
 // building block for the fused pipeline: "gather + inclusive scan"   (the radix sorts live in sort.cu)
 // ------------------------------------------------------------------------------------------------
 struct GatherCount {
-    const int* counts; const unsigned* order;
-    __host__ __device__ int operator()(int j) const { return counts[order[j]]; }
+    const int* counts; const unsigned* order; const int* n_dev;     // n_dev (nullable): items at or past *n_dev count as 0
+    __host__ __device__ int operator()(int j) const
+    {
+#ifdef __CUDA_ARCH__
+        if (n_dev != nullptr && j >= *n_dev) return 0;
+#endif
+        return counts[order[j]];
+    }
 };
 
 extern "C" int lgs_scan_gathered_workspace_bytes(int n, size_t* bytes)
 {
     size_t tmp = 0;
     cub::CountingInputIterator<int> cnt(0);
-    GatherCount op{ nullptr, nullptr };
+    GatherCount op{ nullptr, nullptr, nullptr };
     cub::TransformInputIterator<int, GatherCount, cub::CountingInputIterator<int>> it(cnt, op);
     cub::DeviceScan::InclusiveSum(nullptr, tmp, it, (int*)nullptr, n);
     *bytes = tmp + 256;
@@ -289,12 +318,29 @@ extern "C" int lgs_scan_gathered_workspace_bytes(int n, size_t* bytes)
 }
 
 // out[j] = sum_{k<=j} counts[order[k]]   (inclusive, int32)
+static int scan_gathered(const int* counts, const unsigned* order, int n, const int* n_dev, int* out, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 extern "C" int lgs_scan_gathered(const int* counts, const unsigned* order, int n, int* out, void* workspace, size_t workspace_bytes,
                                  void* stream)
 {
+    return scan_gathered(counts, order, n, nullptr, out, workspace, workspace_bytes, stream);
+}
+
+// capacity items are scanned; items at or past *n_dev contribute 0 (their `order` entries are never read)
+extern "C" int lgs_scan_gathered_dev(const int* counts, const unsigned* order, int capacity, const int* n_dev, int* out, void* workspace,
+                                     size_t workspace_bytes, void* stream)
+{
+    LGS_REQUIRE(n_dev != nullptr, "scan_gathered_dev: n_dev is NULL");
+    return scan_gathered(counts, order, capacity, n_dev, out, workspace, workspace_bytes, stream);
+}
+
+static int scan_gathered(const int* counts, const unsigned* order, int n, const int* n_dev, int* out, void* workspace,
+                         size_t workspace_bytes, void* stream)
+{
     if (n <= 0) return LGS_OK;
     cub::CountingInputIterator<int> cnt(0);
-    GatherCount op{ counts, order };
+    GatherCount op{ counts, order, n_dev };
     cub::TransformInputIterator<int, GatherCount, cub::CountingInputIterator<int>> it(cnt, op);
     size_t need = 0;
     cub::DeviceScan::InclusiveSum(nullptr, need, it, out, n);

@@ -213,11 +213,13 @@ constexpr int LGS_EMIT_WARPS = 8;
 template <int TH, int TW, typename KeyT>
 __global__ void __launch_bounds__(LGS_EMIT_WARPS * 32) emit_pairs_rec_kernel(const SplatRec* __restrict__ recs, const int* __restrict__ offset,
                                                              const unsigned* __restrict__ order, int n, int cap, int H, int W,
-                                                             int gx, int gy, KeyT* __restrict__ keys, int* __restrict__ vals)
+                                                             int gx, int gy, KeyT* __restrict__ keys, int* __restrict__ vals,
+                                                             const int* __restrict__ n_dev)
 {
     __shared__ KeyT s_keys[LGS_EMIT_WARPS][LGS_EMIT_WINDOW];
     __shared__ int s_vals[LGS_EMIT_WARPS][LGS_EMIT_WINDOW];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (n_dev != nullptr) n = min(n, max(*n_dev, 0));         // GPU-driven sizing: n is the capacity, *n_dev the live count
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j - lane >= n) return;                               // whole warp past the end
     int off = 0, asz = 0, i = 0;
@@ -257,7 +259,7 @@ extern "C" int lgs_emit_pairs(const float* packed_params, const int* offset, con
     cudaStream_t st = (cudaStream_t)stream;
     LGS_DISPATCH_TILE(tile_h, tile_w,
         emit_pairs_rec_kernel<TH, TW, int><<<lgs_cdiv(n, LGS_EMIT_WARPS * 32), LGS_EMIT_WARPS * 32, 0, st>>>((const SplatRec*)packed_params, offset, order, n, cap, img_h,
-                                                                           img_w, gx, gy, keys, vals);)
+                                                                           img_w, gx, gy, keys, vals, nullptr);)
     LGS_CHECK_LAUNCH("emit_pairs_rec_kernel");
     return LGS_OK;
 }
@@ -273,8 +275,63 @@ extern "C" int lgs_emit_pairs_u16(const float* packed_params, const int* offset,
     cudaStream_t st = (cudaStream_t)stream;
     LGS_DISPATCH_TILE(tile_h, tile_w,
         emit_pairs_rec_kernel<TH, TW, unsigned short><<<lgs_cdiv(n, LGS_EMIT_WARPS * 32), LGS_EMIT_WARPS * 32, 0, st>>>((const SplatRec*)packed_params, offset, order, n, cap,
-                                                                                      img_h, img_w, gx, gy, keys, vals);)
+                                                                                      img_h, img_w, gx, gy, keys, vals, nullptr);)
     LGS_CHECK_LAUNCH("emit_pairs_rec_kernel<u16>");
+    return LGS_OK;
+}
+
+// GPU-driven forms: n_capacity bounds the launch, *n_dev is the live splat count; pairs past `cap` are dropped (and flagged by
+// lgs_view_params).  key_bits = 16 or 32.
+extern "C" int lgs_emit_pairs_dev(const float* packed_params, const int* offset, const unsigned* order, int n_capacity, const int* n_dev,
+                                  int cap, int img_h, int img_w, int tile_h, int tile_w, int key_bits, void* keys, int* vals, void* stream)
+{
+    LGS_REQUIRE(lgs_tile_ok(tile_h, tile_w), "emit_pairs_dev: tile %dx%d not one of 8x16, 12x16, 16x16, 8x8", tile_h, tile_w);
+    LGS_REQUIRE(n_dev != nullptr && (key_bits == 16 || key_bits == 32), "emit_pairs_dev: bad arguments");
+    if (n_capacity <= 0 || cap <= 0) return LGS_OK;
+    int gx = (img_w + tile_w - 1) / tile_w, gy = (img_h + tile_h - 1) / tile_h;
+    LGS_REQUIRE(key_bits == 32 || gx * gy + 1 < 65536, "emit_pairs_dev: %d tiles do not fit 16-bit keys", gx * gy);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = lgs_cdiv(n_capacity, LGS_EMIT_WARPS * 32);
+    if (key_bits == 16) {
+        LGS_DISPATCH_TILE(tile_h, tile_w,
+            emit_pairs_rec_kernel<TH, TW, unsigned short><<<grid, LGS_EMIT_WARPS * 32, 0, st>>>((const SplatRec*)packed_params, offset, order, n_capacity,
+                                                                                          cap, img_h, img_w, gx, gy, (unsigned short*)keys, vals, n_dev);)
+    } else {
+        LGS_DISPATCH_TILE(tile_h, tile_w,
+            emit_pairs_rec_kernel<TH, TW, int><<<grid, LGS_EMIT_WARPS * 32, 0, st>>>((const SplatRec*)packed_params, offset, order, n_capacity, cap,
+                                                                               img_h, img_w, gx, gy, (int*)keys, vals, n_dev);)
+    }
+    LGS_CHECK_LAUNCH("emit_pairs_rec_kernel(dev)");
+    return LGS_OK;
+}
+
+// Derived launch parameters of one view, computed ON THE DEVICE from the counters project_forward leaves behind, so that the rest
+// of the view can be enqueued without reading anything back:
+//   params[0] = live splat slots (visible chunks * S)      params[1] = pairs, clamped to the pair capacity
+//   params[2] = depth-key bias (smallest key of a splat that owns pairs)
+//   params[3] = bits of the depth-key range                 params[4] = flags: 1 = pairs exceed the capacity (list truncated),
+//   params[5] = pairs (unclamped)                                        2 = depth-key range needs more bits than planned
+//   params[6] = visible chunks                              params[7] = planned depth bits
+// counters = i32[4] as written by lgs_frustum_culling_aabb ([0]) and lgs_project_forward ([1..3]).
+__global__ void view_params_kernel(const int* __restrict__ counters, int S, int pair_capacity, int planned_bits, int* __restrict__ params)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int nvis = counters[0], D = counters[1];
+    const unsigned kmin = ~(unsigned)counters[2], kmax = (unsigned)counters[3];
+    int bits = 1;
+    if (D > 0 && kmax >= kmin) { unsigned r = kmax - kmin; bits = (r == 0) ? 1 : (32 - __clz(r)); }
+    int flags = 0;
+    if (D > pair_capacity) flags |= 1;
+    if (bits > planned_bits) flags |= 2;
+    params[0] = nvis * S; params[1] = min(D, pair_capacity); params[2] = (int)kmin; params[3] = bits;
+    params[4] = flags; params[5] = D; params[6] = nvis; params[7] = planned_bits;
+}
+
+extern "C" int lgs_view_params(const int* counters, int S, int pair_capacity, int planned_depth_bits, int* params, void* stream)
+{
+    LGS_REQUIRE(counters != nullptr && params != nullptr && planned_depth_bits >= 1 && planned_depth_bits <= 32, "view_params: bad arguments");
+    view_params_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counters, S, pair_capacity, planned_depth_bits, params);
+    LGS_CHECK_LAUNCH("view_params_kernel");
     return LGS_OK;
 }
 

@@ -48,16 +48,24 @@ __device__ __forceinline__ unsigned lanemask_lt()
 // shared-memory histograms fed by one ATOMS per key (16-byte key loads when the tile is whole and aligned).
 template <typename KeyT, int IPT, bool VEC>
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const KeyT* __restrict__ keys, int n, int shift, int nbins, int nblocks,
-                                                             int* __restrict__ table, unsigned bias)
+                                                             int* __restrict__ table, unsigned bias, const int* __restrict__ n_dev,
+                                                             const unsigned* __restrict__ bias_dev)
 {
     constexpr int TILE = RS_THREADS * IPT;
     constexpr int KPV = 16 / (int)sizeof(KeyT);                 // keys per 16-byte vector
     __shared__ int h[RS_WARPS][RS_MAXBINS];
     const int t = threadIdx.x, w = t >> 5;
+    // GPU-driven sizing: the launch covers the CAPACITY n, the live count / key bias are read on the device (no host sync)
+    if (n_dev != nullptr) n = min(n, max(*n_dev, 0));
+    if (bias_dev != nullptr) bias = *bias_dev;
+    const int base = blockIdx.x * TILE;
+    if (base >= n) {                                            // block past the live range: an all-zero column
+        if (t < nbins) table[(size_t)t * nblocks + blockIdx.x] = 0;
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < RS_WARPS; k++) h[k][t] = 0;
     __syncthreads();
-    const int base = blockIdx.x * TILE;
     const unsigned mask = (unsigned)nbins - 1u;
     int* hw = h[w];
     if (VEC && base + TILE <= n) {
@@ -113,9 +121,13 @@ template <typename KeyT, int IPT>
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const KeyT* __restrict__ kin, const unsigned* __restrict__ vin,
                                                                 KeyT* __restrict__ kout, unsigned* __restrict__ vout, int n, int shift,
                                                                 int nbins, int nblocks, const int* __restrict__ table,
-                                                                const int* __restrict__ totals, unsigned bias)
+                                                                const int* __restrict__ totals, unsigned bias,
+                                                                const int* __restrict__ n_dev, const unsigned* __restrict__ bias_dev)
 {
     constexpr int TILE = RS_THREADS * IPT;
+    if (n_dev != nullptr) n = min(n, max(*n_dev, 0));
+    if (bias_dev != nullptr) bias = *bias_dev;
+    if ((int)blockIdx.x * TILE >= n) return;
     using BlockScan = cub::BlockScan<int, RS_THREADS>;
     __shared__ int s_cnt[RS_WARPS][RS_MAXBINS];
     __shared__ int s_gofs[RS_MAXBINS];
@@ -224,10 +236,11 @@ RsPlan rs_plan(int n, int begin_bit, int end_bit)
 
 template <typename KeyT>
 int rs_sort(const KeyT* keys_in, KeyT* keys_out, const unsigned* vals_in, unsigned* vals_out, int n, int begin_bit, int end_bit,
-            unsigned bias, char* ws, cudaStream_t st)
+            unsigned bias, char* ws, cudaStream_t st, const int* n_dev = nullptr, const unsigned* bias_dev = nullptr)
 {
     RsPlan p = rs_plan<KeyT>(n, begin_bit, end_bit);
     if (p.passes == 0) {
+        LGS_REQUIRE(n_dev == nullptr, "sort_pairs: a device-side count needs at least one pass");
         LGS_CUDA(cudaMemcpyAsync(keys_out, keys_in, (size_t)n * sizeof(KeyT), cudaMemcpyDeviceToDevice, st));
         LGS_CUDA(cudaMemcpyAsync(vals_out, vals_in, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
         return LGS_OK;
@@ -247,17 +260,17 @@ int rs_sort(const KeyT* keys_in, KeyT* keys_out, const unsigned* vals_in, unsign
         unsigned* vdst = to_out ? vals_out : vtmp;
         const bool vec = ((uintptr_t)ksrc & 15) == 0;
         if (p.ipt == 16) {
-            if (vec) rs_hist_kernel<KeyT, 16, true><<<p.nblocks, RS_THREADS, 0, st>>>(ksrc, n, bit, nbins, p.nblocks, table, bias);
-            else rs_hist_kernel<KeyT, 16, false><<<p.nblocks, RS_THREADS, 0, st>>>(ksrc, n, bit, nbins, p.nblocks, table, bias);
+            if (vec) rs_hist_kernel<KeyT, 16, true><<<p.nblocks, RS_THREADS, 0, st>>>(ksrc, n, bit, nbins, p.nblocks, table, bias, n_dev, bias_dev);
+            else rs_hist_kernel<KeyT, 16, false><<<p.nblocks, RS_THREADS, 0, st>>>(ksrc, n, bit, nbins, p.nblocks, table, bias, n_dev, bias_dev);
         } else {
-            if (vec) rs_hist_kernel<KeyT, 8, true><<<p.nblocks, RS_THREADS, 0, st>>>(ksrc, n, bit, nbins, p.nblocks, table, bias);
-            else rs_hist_kernel<KeyT, 8, false><<<p.nblocks, RS_THREADS, 0, st>>>(ksrc, n, bit, nbins, p.nblocks, table, bias);
+            if (vec) rs_hist_kernel<KeyT, 8, true><<<p.nblocks, RS_THREADS, 0, st>>>(ksrc, n, bit, nbins, p.nblocks, table, bias, n_dev, bias_dev);
+            else rs_hist_kernel<KeyT, 8, false><<<p.nblocks, RS_THREADS, 0, st>>>(ksrc, n, bit, nbins, p.nblocks, table, bias, n_dev, bias_dev);
         }
         LGS_CHECK_LAUNCH("rs_hist_kernel");
         rs_scan_rows_kernel<<<nbins, RS_THREADS, 0, st>>>(table, p.nblocks, totals);
         LGS_CHECK_LAUNCH("rs_scan_rows_kernel");
-        if (p.ipt == 16) rs_scatter_kernel<KeyT, 16><<<p.nblocks, RS_THREADS, 0, st>>>(ksrc, vsrc, kdst, vdst, n, bit, nbins, p.nblocks, table, totals, bias);
-        else rs_scatter_kernel<KeyT, 8><<<p.nblocks, RS_THREADS, 0, st>>>(ksrc, vsrc, kdst, vdst, n, bit, nbins, p.nblocks, table, totals, bias);
+        if (p.ipt == 16) rs_scatter_kernel<KeyT, 16><<<p.nblocks, RS_THREADS, 0, st>>>(ksrc, vsrc, kdst, vdst, n, bit, nbins, p.nblocks, table, totals, bias, n_dev, bias_dev);
+        else rs_scatter_kernel<KeyT, 8><<<p.nblocks, RS_THREADS, 0, st>>>(ksrc, vsrc, kdst, vdst, n, bit, nbins, p.nblocks, table, totals, bias, n_dev, bias_dev);
         LGS_CHECK_LAUNCH("rs_scatter_kernel");
         ksrc = kdst; vsrc = vdst;
         bit += dbits;
@@ -347,4 +360,57 @@ extern "C" int lgs_sort_pairs_u16(const unsigned short* keys_in, unsigned short*
 {
     return sort_pairs<unsigned short>("sort_pairs_u16", keys_in, keys_out, vals_in, vals_out, n, begin_bit, end_bit, 0u, workspace,
                                       workspace_bytes, stream);
+}
+
+// ---- GPU-driven variants: capacity on the host, live count (and key bias) on the device -------------------------------------
+// The launch geometry covers `capacity` items; every kernel reads the live count from *n_dev (clamped to the capacity) and,
+// for the rebased depth sort, the bias from *bias_dev -- no read-back, so a whole view can be enqueued (or captured in a
+// CUDA graph) without a host synchronisation (SURVEY 7 "GPU-driven sizing"; the reference hides its two read-backs behind last
+// epoch's feedback values instead, GR/compact.cu:527-549, GR/binning.cu:137-163).  Own radix sort only.
+extern "C" int lgs_sort_pairs_u32_dev(const unsigned* keys_in, unsigned* keys_out, const unsigned* vals_in, unsigned* vals_out,
+                                      int capacity, const int* n_dev, const unsigned* bias_dev, int end_bit, void* workspace,
+                                      size_t workspace_bytes, void* stream)
+{
+    if (capacity <= 0) return LGS_OK;
+    LGS_REQUIRE(n_dev != nullptr && end_bit >= 1 && end_bit <= 32, "sort_pairs_u32_dev: bad arguments (end_bit %d)", end_bit);
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    size_t need = rs_plan<unsigned>(capacity, 0, end_bit).total_bytes;
+    if (workspace == nullptr || workspace_bytes < need + 256) {
+        lgs_set_error("sort_pairs_u32_dev: workspace of %zu bytes needed, %zu given", need + 256, workspace_bytes);
+        return LGS_ERR_WORKSPACE;
+    }
+    return rs_sort<unsigned>(keys_in, keys_out, vals_in, vals_out, capacity, 0, end_bit, 0u, ws, (cudaStream_t)stream, n_dev, bias_dev);
+}
+
+extern "C" int lgs_sort_pairs_u16_dev(const unsigned short* keys_in, unsigned short* keys_out, const unsigned* vals_in,
+                                      unsigned* vals_out, int capacity, const int* n_dev, int begin_bit, int end_bit, void* workspace,
+                                      size_t workspace_bytes, void* stream)
+{
+    if (capacity <= 0) return LGS_OK;
+    LGS_REQUIRE(n_dev != nullptr && begin_bit >= 0 && end_bit > begin_bit && end_bit <= 16, "sort_pairs_u16_dev: bad bit range [%d, %d)",
+                begin_bit, end_bit);
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    size_t need = rs_plan<unsigned short>(capacity, begin_bit, end_bit).total_bytes;
+    if (workspace == nullptr || workspace_bytes < need + 256) {
+        lgs_set_error("sort_pairs_u16_dev: workspace of %zu bytes needed, %zu given", need + 256, workspace_bytes);
+        return LGS_ERR_WORKSPACE;
+    }
+    return rs_sort<unsigned short>(keys_in, keys_out, vals_in, vals_out, capacity, begin_bit, end_bit, 0u, ws, (cudaStream_t)stream, n_dev,
+                                   nullptr);
+}
+
+extern "C" int lgs_sort_pairs_u32k_dev(const unsigned* keys_in, unsigned* keys_out, const unsigned* vals_in, unsigned* vals_out,
+                                       int capacity, const int* n_dev, int begin_bit, int end_bit, void* workspace, size_t workspace_bytes,
+                                       void* stream)
+{   // 32-bit tile keys (more than 65534 tiles), device-side count
+    if (capacity <= 0) return LGS_OK;
+    LGS_REQUIRE(n_dev != nullptr && begin_bit >= 0 && end_bit > begin_bit && end_bit <= 32, "sort_pairs_u32k_dev: bad bit range [%d, %d)",
+                begin_bit, end_bit);
+    char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    size_t need = rs_plan<unsigned>(capacity, begin_bit, end_bit).total_bytes;
+    if (workspace == nullptr || workspace_bytes < need + 256) {
+        lgs_set_error("sort_pairs_u32k_dev: workspace of %zu bytes needed, %zu given", need + 256, workspace_bytes);
+        return LGS_ERR_WORKSPACE;
+    }
+    return rs_sort<unsigned>(keys_in, keys_out, vals_in, vals_out, capacity, begin_bit, end_bit, 0u, ws, (cudaStream_t)stream, n_dev, nullptr);
 }
