@@ -151,6 +151,10 @@ class StageTimer:
                     timer.sort_kernels += 3 * ((int(a[6]) - int(a[5]) + 7) // 8)
                 elif name == "lgs_sort_pairs_u32_rebased":
                     timer.sort_kernels += 3 * ((int(a[6]) + 7) // 8)
+                elif name == "lgs_sort_pairs_u32_dev":
+                    timer.sort_kernels += 3 * ((int(a[7]) + 7) // 8)
+                elif name in ("lgs_sort_pairs_u16_dev", "lgs_sort_pairs_u32k_dev"):
+                    timer.sort_kernels += 3 * ((int(a[7]) - int(a[6]) + 7) // 8)
         _lib.call = call
 
     def summary(self):
@@ -438,7 +442,7 @@ def run_ours(args, rank, world, local_rank):
         if args.level == "B":
             return render.render_views(vpr, camera_fn, loss_fn, A[0], A[1], P["xyz"], P["scale"], P["rot"], P["sh_0"], P["sh_rest"],
                                        P["opacity"], args.sh_degree, (H, W), pp, acc_views_all[step_no["k"] % len(accs)],
-                                       n_streams=1 if serial else n_streams)
+                                       n_streams=n_streams)
         return [render_one_level_a(camera_fn(j), loss_fn(j, None)) for j in range(vpr)]
 
     def reduce_step(a, record):
@@ -496,7 +500,10 @@ def run_ours(args, rank, world, local_rank):
     comm_ms = sum(a_.elapsed_time(b_) for a_, b_ in comm_events) / max(1, len(comm_events)) if comm_events else 0.0
     # stage attribution / roofline durations: the same steps once more on ONE stream with CUDA events around every
     # C-ABI call (with overlapping streams a kernel's event-to-event time includes the other stream's work).
+    # (CUDA graphs off and one view at a time on ONE stream for this pass: the C-ABI calls have to be visible one by one)
     timer.enabled = True
+    graphs_keep, n_streams_keep = pipeline.GRAPHS_ENABLED, n_streams
+    pipeline.GRAPHS_ENABLED, n_streams = False, 1
     s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
     s0.record()
     for _ in range(args.steps):
@@ -504,6 +511,7 @@ def run_ours(args, rank, world, local_rank):
     s1.record()
     barrier()
     timer.enabled = False
+    pipeline.GRAPHS_ENABLED, n_streams = graphs_keep, n_streams_keep
     ms_serial = s0.elapsed_time(s1)
     # max over ranks of the step time; per-rank render time and all-reduce time gathered for the imbalance / limiter report
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -586,13 +594,14 @@ def run_ours(args, rank, world, local_rank):
 
         def e2e_loss(j, img):       # H2D of the uint8 target, loss, D2H of the result
             gt = gt_host[j % 2].to(dev, non_blocking=True)
-            # loss = sum(img * (gt/255 - 0.5)): the uint8 -> float conversion is one kernel (gt - 127.5), the 1/255 scales the sum
-            weight = torch.sub(gt, 127.5)
+            # loss = sum(img * (gt/255 - 0.5)) and its gradient (gt - 127.5)/255, handed to the rasterizer directly
+            # (render_views' loss-and-gradient form): two elementwise kernels and one dot product per view
+            d_img = torch.sub(gt, 127.5).mul_(1.0 / 255.0)
             if img is None:
-                return weight * (1.0 / 255.0)
-            loss = (img * weight).sum() * (1.0 / 255.0)
-            loss_hosts[step_no["k"] % 2][j:j + 1].copy_(loss.detach().reshape(1), non_blocking=True)
-            return loss
+                return d_img
+            loss = torch.dot(img.reshape(-1), d_img.reshape(-1))
+            loss_hosts[step_no["k"] % 2][j:j + 1].copy_(loss.reshape(1), non_blocking=True)
+            return loss, d_img
 
         def read_losses(k):         # D2H results of step k: wait for its event, then read the pinned buffer
             loss_ev[k % 2].synchronize()
@@ -656,9 +665,14 @@ def run_ours(args, rank, world, local_rank):
     for name, (tot, n) in summ.items():
         stages[name] = {"ms_per_view": tot / n_views_rank, "launches_per_view": n / n_views_rank}
     for old, new in (("lgs_sort_pairs_u32_rebased", "lgs_sort_pairs_u32(depth)"), ("lgs_sort_pairs_u32", "lgs_sort_pairs_u32(tile)"),
-                     ("lgs_sort_pairs_u16", "lgs_sort_pairs_u16(tile)")):
-        if old in stages:
+                     ("lgs_sort_pairs_u16", "lgs_sort_pairs_u16(tile)"), ("lgs_sort_pairs_u32_dev", "lgs_sort_pairs_u32(depth)"),
+                     ("lgs_sort_pairs_u16_dev", "lgs_sort_pairs_u16(tile)"), ("lgs_sort_pairs_u32k_dev", "lgs_sort_pairs_u32(tile)"),
+                     ("lgs_scan_gathered_dev", "lgs_scan_gathered"), ("lgs_tile_range_u16_dev", "lgs_tile_range_u16"),
+                     ("lgs_tile_range_dev", "lgs_tile_range")):
+        if old in stages:                       # the GPU-driven (device-side count) entry points are the same kernels
             stages[new] = stages.pop(old)
+    if "lgs_emit_pairs_dev" in stages:
+        stages["lgs_emit_pairs_u16" if (stats["tiles"] + 1) < 65536 else "lgs_emit_pairs"] = stages.pop("lgs_emit_pairs_dev")
     for name, s_ in stages.items():
         b = bytes_per.get(name)
         if b is not None and s_["ms_per_view"] > 0:
@@ -702,7 +716,8 @@ def run_ours(args, rank, world, local_rank):
             "ms_per_view": ms_view, "ms_per_view_single_stream": ms_view_serial}
     hand_written = ("lgs_frustum_culling_aabb", "lgs_project_forward", "lgs_emit_pairs", "lgs_emit_pairs_u16", "lgs_tile_range",
                     "lgs_tile_range_u16", "lgs_rasterize_forward_packed", "lgs_rasterize_backward", "lgs_project_backward",
-                    "lgs_sparse_chunk_op", "lgs_pack_params", "lgs_tile_order")
+                    "lgs_sparse_chunk_op", "lgs_pack_params", "lgs_tile_order", "lgs_emit_pairs_dev", "lgs_tile_range_u16_dev",
+                    "lgs_tile_range_dev", "lgs_view_params")
     gpu_launches = 0
     for name, (tot, n) in summ.items():
         if name in hand_written:
@@ -731,6 +746,7 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "inputs exceed L2 (236 MB of parameters streamed per view); no explicit flush",
                    "staging": args.staging or os.environ.get("LGS_STAGING", "default"), "streams": n_streams,
                    "backward_kernel": os.environ.get("LGS_BWD", "v2"), "tile_order": os.environ.get("LGS_TILE_ORDER", "1") != "0",
+                   "gpu_driven_sizing": bool(pipeline.SYNC_FREE and args.level == "B"), "cuda_graphs": bool(pipeline.GRAPHS_ENABLED and pipeline.SYNC_FREE and args.level == "B" and n_streams > 1),
                    "stage_timing": "serialized pass of the same steps on one stream (CUDA events around every C-ABI call)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches),
         "roofline": roofline, "roofline_issue": roofline_issue, "path_roofline": path, "workload_stats": stats, "stages": stages,

@@ -163,7 +163,8 @@ int lgs_scan_gathered(const int* counts, const unsigned* order, int n, int* out,
  * feedback buffers (GR/compact.cu:527-549, GR/binning.cu:137-163, data.py:238); here the capacity is the caller's prediction
  * and lgs_view_params raises a device-side flag when it was too small. */
 int lgs_view_params(const int* counters /* i32[4]: visible chunks, pairs, ~min depth key, max depth key */, int S, int pair_capacity,
-                    int planned_depth_bits, int* params /* i32[8], see csrc/fused.cu */, void* stream);
+                    int planned_depth_bits, int* params /* i32[8], see csrc/fused.cu */,
+                    int* sticky /* nullable i32[4]: |= flags, max pairs, max depth bits, views -- accumulated over views */, void* stream);
 int lgs_sort_pairs_u32_dev(const unsigned* keys_in, unsigned* keys_out, const unsigned* vals_in, unsigned* vals_out, int capacity,
                            const int* n_dev, const unsigned* bias_dev, int end_bit, void* workspace, size_t workspace_bytes, void* stream);
 int lgs_sort_pairs_u16_dev(const unsigned short* keys_in, unsigned short* keys_out, const unsigned* vals_in, unsigned* vals_out,

@@ -43,7 +43,7 @@ SIGNATURES = {
     "lgs_sort_pairs_u32_rebased": [_P, _P, _P, _P, _I, ctypes.c_uint, _I, _P, _Z, _P],
     "lgs_scan_gathered_workspace_bytes": [_I, ctypes.POINTER(_Z)],
     "lgs_scan_gathered": [_P, _P, _I, _P, _P, _Z, _P],
-    "lgs_view_params": [_P, _I, _I, _I, _P, _P],
+    "lgs_view_params": [_P, _I, _I, _I, _P, _P, _P],
     "lgs_sort_pairs_u32_dev": [_P, _P, _P, _P, _I, _P, _P, _I, _P, _Z, _P],
     "lgs_sort_pairs_u16_dev": [_P, _P, _P, _P, _I, _P, _I, _I, _P, _Z, _P],
     "lgs_sort_pairs_u32k_dev": [_P, _P, _P, _P, _I, _P, _I, _I, _P, _Z, _P],

@@ -313,7 +313,10 @@ extern "C" int lgs_emit_pairs_dev(const float* packed_params, const int* offset,
 //   params[5] = pairs (unclamped)                                        2 = depth-key range needs more bits than planned
 //   params[6] = visible chunks                              params[7] = planned depth bits
 // counters = i32[4] as written by lgs_frustum_culling_aabb ([0]) and lgs_project_forward ([1..3]).
-__global__ void view_params_kernel(const int* __restrict__ counters, int S, int pair_capacity, int planned_bits, int* __restrict__ params)
+// sticky (i32[4], nullable) accumulates over views: [0] |= flags, [1] = max pairs, [2] = max depth bits, [3] += 1 -- one read-back
+// per BATCH of views tells whether any of them overflowed and how large the next workspace has to be.
+__global__ void view_params_kernel(const int* __restrict__ counters, int S, int pair_capacity, int planned_bits, int* __restrict__ params,
+                                   int* __restrict__ sticky)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const int nvis = counters[0], D = counters[1];
@@ -325,12 +328,16 @@ __global__ void view_params_kernel(const int* __restrict__ counters, int S, int 
     if (bits > planned_bits) flags |= 2;
     params[0] = nvis * S; params[1] = min(D, pair_capacity); params[2] = (int)kmin; params[3] = bits;
     params[4] = flags; params[5] = D; params[6] = nvis; params[7] = planned_bits;
+    if (sticky != nullptr) {
+        atomicOr(&sticky[0], flags); atomicMax(&sticky[1], D); atomicMax(&sticky[2], bits); atomicAdd(&sticky[3], 1);
+    }
 }
 
-extern "C" int lgs_view_params(const int* counters, int S, int pair_capacity, int planned_depth_bits, int* params, void* stream)
+extern "C" int lgs_view_params(const int* counters, int S, int pair_capacity, int planned_depth_bits, int* params, int* sticky,
+                               void* stream)
 {
     LGS_REQUIRE(counters != nullptr && params != nullptr && planned_depth_bits >= 1 && planned_depth_bits <= 32, "view_params: bad arguments");
-    view_params_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counters, S, pair_capacity, planned_depth_bits, params);
+    view_params_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counters, S, pair_capacity, planned_depth_bits, params, sticky);
     LGS_CHECK_LAUNCH("view_params_kernel");
     return LGS_OK;
 }

@@ -255,10 +255,55 @@ def render_views(n_views: int, camera_fn, loss_fn, cluster_origin, cluster_exten
             loss.backward()
         losses.append(loss.detach())
 
-    one = one_direct if direct else one_autograd
+    # GPU-driven path (default): one preallocated ViewWorkspace per stream slot, no host synchronisation inside the batch, the
+    # per-view forward / backward replayed as CUDA graphs.  The first batch of a configuration goes through the synchronising
+    # path and measures the capacities (the reference's cold first epoch); statistics runs keep the synchronising path.
+    slots = None
+    if direct and pipeline.SYNC_FREE and not stat:
+        slots = _view_slots(params, (H, W), (th, tw), max(1, n_streams))
+    probe = {"pairs": 0, "bits": 1} if (slots is not None and slots.ws is None) else None
+
+    def one_ws(i, wait_ev, ws):
+        cam = camera_fn(i)
+        img_p = ws.forward(params, cluster_origin, cluster_extend, cam, int(actived_sh_degree), clamp_zero=True)
+        if loss_and_grad_fn is not None:
+            loss, d_img = loss_and_grad_fn(i, img_p[..., :H, :W])
+        else:
+            leaf = img_p[..., :H, :W].detach().requires_grad_(True)
+            loss = loss_fn(i, leaf)
+            if isinstance(loss, tuple):
+                loss, d_img = loss
+            else:
+                (d_img,) = torch.autograd.grad(loss, leaf)
+        if wait_ev is not None:
+            torch.cuda.current_stream(dev).wait_event(wait_ev)
+        ws.backward(params, d_img, int(actived_sh_degree), accumulate_into, use_clamp=True)
+        losses.append(loss.detach())
+
+    def one_probe(i, wait_ev):
+        n0 = len(pipeline.LAST_VIEW_SIZES)
+        one_direct(i, wait_ev)
+        for pairs, bits in pipeline.LAST_VIEW_SIZES[n0:]:
+            probe["pairs"] = max(probe["pairs"], pairs); probe["bits"] = max(probe["bits"], bits)
+        del pipeline.LAST_VIEW_SIZES[:]
+
+    if slots is not None and slots.ws is not None:
+        slots.check()
+        one = None
+    elif probe is not None:
+        one = one_probe
+    else:
+        one = one_direct if direct else one_autograd
     if n_streams <= 1:
         for i in range(n_views):
-            one(i, None)
+            if one is None:
+                one_ws(i, None, slots.ws[0])
+            else:
+                one(i, None)
+        if one is None:
+            slots.ws[0].post_flags()
+        elif probe is not None:
+            slots.size(probe["pairs"], probe["bits"])
         return losses
     cur = torch.cuda.current_stream(dev)
     side = _streams(dev, n_streams)
@@ -268,9 +313,81 @@ def render_views(n_views: int, camera_fn, loss_fn, cluster_origin, cluster_exten
     for i in range(n_views):
         s = side[i % n_streams]
         with torch.cuda.stream(s):
-            one(i, prev)
+            if one is None:
+                one_ws(i, prev, slots.ws[i % n_streams])
+            else:
+                one(i, prev)
             prev = torch.cuda.Event()
             prev.record(s)
+    if one is None:
+        for k, s in enumerate(side[: min(n_streams, n_views)]):
+            with torch.cuda.stream(s):
+                slots.ws[k].post_flags()
+    elif probe is not None:
+        slots.size(probe["pairs"], probe["bits"])
     for s in side:
         cur.wait_stream(s)
     return losses
+
+
+class _ViewSlots:
+    """The per-configuration state of render_views' GPU-driven path: capacities measured by the first (synchronising) batch and
+    one ViewWorkspace per stream slot, created from them."""
+
+    def __init__(self, params, hw, tile):
+        self.params_like, self.hw, self.tile = params, hw, tile
+        self.ws = None
+        self.cap, self.bits = 0, 24
+
+    def size(self, max_pairs, max_bits):
+        """Capacities from the measured maxima: 30 % head-room on the pairs, the depth range rounded up to whole 8-bit passes with
+        at least one spare bit."""
+        self.cap = int(max_pairs * 1.3) + 65536
+        self.bits = min(32, 8 * ((max_bits + 1 + 7) // 8))
+        self.ws = []
+
+    def ensure(self, n_slots):
+        """One workspace per stream slot (created on demand once the capacities are known)."""
+        while self.ws is not None and len(self.ws) < n_slots:
+            self.ws.append(pipeline.ViewWorkspace(self.params_like, self.hw, self.tile, self.cap, self.bits))
+
+    def check(self):
+        """Overflow flags of the previous batch (if they have landed): on overflow drop the workspaces -- the next batch measures
+        again -- and tell the caller to redo the step."""
+        try:
+            for w in self.ws:
+                w.check(wait=False)
+        except pipeline.CapacityExceeded:
+            self.ws = None
+            raise
+
+
+_slot_cache: dict = {}
+
+
+def _view_slots(params, hw, tile, n_slots):
+    xyz = params["xyz"]
+    key = (xyz.device, tuple(xyz.shape[-2:]), hw, tile, params["sh_rest"].shape[0])
+    ent = _slot_cache.get(key)
+    if ent is None:
+        ent = _slot_cache[key] = _ViewSlots(params, hw, tile)
+    ent.ensure(n_slots)
+    return ent
+
+
+def check_views(wait: bool = True):
+    """Explicit form of the lazy overflow check of render_views' GPU-driven path: (after a synchronisation) raises
+    pipeline.CapacityExceeded if a view of the last batch overflowed its workspace -- redo that step."""
+    for ent in _slot_cache.values():
+        if ent.ws is not None:
+            try:
+                for w in ent.ws:
+                    w.check(wait=wait)
+            except pipeline.CapacityExceeded:
+                ent.ws = None
+                raise
+
+
+def reset_view_workspaces():
+    """Forget every cached workspace / CUDA graph (call after the scene's size changed, e.g. densification)."""
+    _slot_cache.clear()
