@@ -22,13 +22,13 @@ from litegs_b200.arguments import PipelineParams  # noqa: E402
 from litegs_b200.dist import PARAM_ORDER  # noqa: E402
 
 
-def make_dataset(root, n_gaussians=60_000, n_views=24, hw=(270, 480), n_points=20_000, seed=0, dev=None):
+def make_dataset(root, n_gaussians=60_000, n_views=24, hw=(270, 480), n_points=20_000, seed=0, dev=None, log_scale_range=(0.01, 0.04)):
     """A hidden scene rendered from the lattice cameras -> COLMAP model + PNGs.  The 'SfM points' are a subsample of the
     hidden Gaussians' centres with their band-0 colours (what a real reconstruction would roughly deliver)."""
     dev = dev or torch.device("cuda:0")
     H, W = hw
     pp = PipelineParams(tile_size=(8, 16), sparse_grad=True)
-    truth = scene.make_scene(n_gaussians, sh_degree=3, seed=seed, log_scale_range=(0.01, 0.04))
+    truth = scene.make_scene(n_gaussians, sh_degree=3, seed=seed, log_scale_range=log_scale_range)
     T = {k: torch.from_numpy(truth[k]).to(dev) for k in PARAM_ORDER}
     A = [torch.from_numpy(truth[k]).to(dev) for k in ("cluster_origin", "cluster_extend")]
 
@@ -67,6 +67,8 @@ def load_dataset(root, image_dir="images", dev=None):
 def train(root, iters=300, views_per_step=8, log=print):
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
     torch.cuda.set_device(dev)
+    from litegs_b200 import fused
+    fused.CONFIG["true_sigmoid_grad"] = True               # our own loops train with the true sigmoid derivative
     frames, xyz, rgb = load_dataset(root, dev=dev)
     H, W = frames[0][2]
     g = colmap.gaussians_from_points(xyz, rgb, sh_degree=3)

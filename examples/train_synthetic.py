@@ -17,7 +17,7 @@ import time
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from litegs_b200 import dist as lgs_dist, optimizer, render, scene, ssim  # noqa: E402
+from litegs_b200 import dist as lgs_dist, fused, optimizer, render, scene, ssim  # noqa: E402
 from litegs_b200.arguments import PipelineParams  # noqa: E402
 from litegs_b200.dist import PARAM_ORDER  # noqa: E402
 
@@ -35,7 +35,8 @@ def train(n_gaussians=50_000, hw=(270, 480), n_views=16, iters=100, seed=0, devi
     T = {k: torch.from_numpy(truth[k]).to(dev) for k in PARAM_ORDER}
     A = [torch.from_numpy(truth[k]).to(dev) for k in ("cluster_origin", "cluster_extend")]
     cams = [{k: torch.from_numpy(v).to(dev) for k, v in scene.make_camera(j, n_views, W, H).items()} for j in range(n_views)]
-    mine = lgs_dist.shard_views(n_views, rank, world)
+    mine = lgs_dist.shard_views(n_views, rank, world)      # shards may differ by one view: the loss is the mean over ALL n_views
+    fused.CONFIG["true_sigmoid_grad"] = True               # our own loops train with the true sigmoid derivative
     with torch.no_grad():       # targets: renders of the true scene
         gts = {j: render.render_view(A[0], A[1], cams[j]["frustumplane"], cams[j]["view"], cams[j]["proj"], T["xyz"], T["scale"], T["rot"],
                                      T["sh_0"], T["sh_rest"], T["opacity"], 3, (H, W), pp)[0].contiguous() for j in mine}
@@ -54,14 +55,16 @@ def train(n_gaussians=50_000, hw=(270, 480), n_views=16, iters=100, seed=0, devi
                                      A[0], A[1], P["xyz"], P["scale"], P["rot"], P["sh_0"], P["sh_rest"], P["opacity"], 3, (H, W), pp,
                                      acc.grads(),
                                      loss_and_grad_fn=lambda i, img: ssim.l1_ssim_loss_and_grad(img.contiguous(), gts[mine[i]], 0.2,
-                                                                                              upstream=1.0 / (len(mine) * world)))
+                                                                                              upstream=1.0 / n_views))
         acc.all_reduce()
         opt.step(acc)
         sched.step()
-        history.append(float(torch.stack(losses).mean()))
-        if rank == 0 and (it % 20 == 0 or it == iters - 1):
-            log(f"iter {it:4d}  loss {history[-1]:.5f}")
+        history.append(torch.stack(losses).mean())          # stays on the device: no host synchronisation inside the loop
+        if rank == 0 and (it % 50 == 0 or it == iters - 1):
+            log(f"iter {it:4d}  loss {float(history[-1]):.5f}")
     torch.cuda.synchronize(dev)
+    render.check_views()                                    # GPU-driven sizing: no view of the run outgrew its workspace
+    history = [float(h) for h in history]
     if rank == 0:
         dt = time.perf_counter() - t0
         log(f"{iters} iterations x {len(mine)} views x {world} ranks in {dt:.2f} s = {iters * len(mine) * world / dt:.1f} views/s (loss + optimizer included)")

@@ -175,7 +175,8 @@ int lgs_sort_pairs_u32k_dev(const unsigned* keys_in, unsigned* keys_out, const u
 int lgs_scan_gathered_dev(const int* counts, const unsigned* order, int capacity, const int* n_dev, int* out, void* workspace,
                           size_t workspace_bytes, void* stream);
 int lgs_emit_pairs_dev(const float* packed_params, const int* offset, const unsigned* order, int n_capacity, const int* n_dev, int cap,
-                       int img_h, int img_w, int tile_h, int tile_w, int key_bits /* 16 | 32 */, void* keys, int* vals, void* stream);
+                       int img_h, int img_w, int tile_h, int tile_w, int key_bits /* 16 | 32 */, void* keys, int* vals,
+                       int* valid_pairs /* nullable: lowered to the written length when runs were dropped */, void* stream);
 int lgs_tile_range_u16_dev(const unsigned short* table_tile_id, int capacity, const int* length_dev, int max_tile_id, int fix_last,
                            int* tile_range, void* stream);
 int lgs_tile_range_dev(const int* table_tile_id, int capacity, const int* length_dev, int max_tile_id, int fix_last, int* tile_range,

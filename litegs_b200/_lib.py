@@ -48,7 +48,7 @@ SIGNATURES = {
     "lgs_sort_pairs_u16_dev": [_P, _P, _P, _P, _I, _P, _I, _I, _P, _Z, _P],
     "lgs_sort_pairs_u32k_dev": [_P, _P, _P, _P, _I, _P, _I, _I, _P, _Z, _P],
     "lgs_scan_gathered_dev": [_P, _P, _I, _P, _P, _P, _Z, _P],
-    "lgs_emit_pairs_dev": [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "lgs_emit_pairs_dev": [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "lgs_tile_range_u16_dev": [_P, _I, _P, _I, _I, _P, _P],
     "lgs_tile_range_dev": [_P, _I, _P, _I, _I, _P, _P],
     "lgs_pack_params": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P],

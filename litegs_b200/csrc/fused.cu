@@ -214,7 +214,7 @@ template <int TH, int TW, typename KeyT>
 __global__ void __launch_bounds__(LGS_EMIT_WARPS * 32) emit_pairs_rec_kernel(const SplatRec* __restrict__ recs, const int* __restrict__ offset,
                                                              const unsigned* __restrict__ order, int n, int cap, int H, int W,
                                                              int gx, int gy, KeyT* __restrict__ keys, int* __restrict__ vals,
-                                                             const int* __restrict__ n_dev)
+                                                             const int* __restrict__ n_dev, int* __restrict__ valid_pairs)
 {
     __shared__ KeyT s_keys[LGS_EMIT_WARPS][LGS_EMIT_WINDOW];
     __shared__ int s_vals[LGS_EMIT_WARPS][LGS_EMIT_WINDOW];
@@ -226,6 +226,9 @@ __global__ void __launch_bounds__(LGS_EMIT_WARPS * 32) emit_pairs_rec_kernel(con
     if (j < n) {
         off = j == 0 ? 0 : offset[j - 1];
         asz = offset[j] - off;
+        // the first run that crosses the capacity: everything from here on is dropped, so the list is valid up to `off`
+        // exactly (offsets are monotone: this thread is unique) -- the sort and the tile ranges must not look further
+        if (valid_pairs != nullptr && asz > 0 && off <= cap && off + asz > cap) *valid_pairs = off;
         if (asz <= 0 || off + asz > cap) asz = 0;
         i = (int)order[j];
     }
@@ -259,7 +262,7 @@ extern "C" int lgs_emit_pairs(const float* packed_params, const int* offset, con
     cudaStream_t st = (cudaStream_t)stream;
     LGS_DISPATCH_TILE(tile_h, tile_w,
         emit_pairs_rec_kernel<TH, TW, int><<<lgs_cdiv(n, LGS_EMIT_WARPS * 32), LGS_EMIT_WARPS * 32, 0, st>>>((const SplatRec*)packed_params, offset, order, n, cap, img_h,
-                                                                           img_w, gx, gy, keys, vals, nullptr);)
+                                                                           img_w, gx, gy, keys, vals, nullptr, nullptr);)
     LGS_CHECK_LAUNCH("emit_pairs_rec_kernel");
     return LGS_OK;
 }
@@ -275,15 +278,17 @@ extern "C" int lgs_emit_pairs_u16(const float* packed_params, const int* offset,
     cudaStream_t st = (cudaStream_t)stream;
     LGS_DISPATCH_TILE(tile_h, tile_w,
         emit_pairs_rec_kernel<TH, TW, unsigned short><<<lgs_cdiv(n, LGS_EMIT_WARPS * 32), LGS_EMIT_WARPS * 32, 0, st>>>((const SplatRec*)packed_params, offset, order, n, cap,
-                                                                                      img_h, img_w, gx, gy, keys, vals, nullptr);)
+                                                                                      img_h, img_w, gx, gy, keys, vals, nullptr, nullptr);)
     LGS_CHECK_LAUNCH("emit_pairs_rec_kernel<u16>");
     return LGS_OK;
 }
 
-// GPU-driven forms: n_capacity bounds the launch, *n_dev is the live splat count; pairs past `cap` are dropped (and flagged by
-// lgs_view_params).  key_bits = 16 or 32.
+// GPU-driven forms: n_capacity bounds the launch, *n_dev is the live splat count; runs that would cross `cap` are dropped (and
+// flagged by lgs_view_params) and *valid_pairs (nullable; normally &params[1]) is lowered to the length of the list that WAS
+// written, so that nothing downstream reads an unwritten slot.  key_bits = 16 or 32.
 extern "C" int lgs_emit_pairs_dev(const float* packed_params, const int* offset, const unsigned* order, int n_capacity, const int* n_dev,
-                                  int cap, int img_h, int img_w, int tile_h, int tile_w, int key_bits, void* keys, int* vals, void* stream)
+                                  int cap, int img_h, int img_w, int tile_h, int tile_w, int key_bits, void* keys, int* vals,
+                                  int* valid_pairs, void* stream)
 {
     LGS_REQUIRE(lgs_tile_ok(tile_h, tile_w), "emit_pairs_dev: tile %dx%d not one of 8x16, 12x16, 16x16, 8x8", tile_h, tile_w);
     LGS_REQUIRE(n_dev != nullptr && (key_bits == 16 || key_bits == 32), "emit_pairs_dev: bad arguments");
@@ -295,11 +300,11 @@ extern "C" int lgs_emit_pairs_dev(const float* packed_params, const int* offset,
     if (key_bits == 16) {
         LGS_DISPATCH_TILE(tile_h, tile_w,
             emit_pairs_rec_kernel<TH, TW, unsigned short><<<grid, LGS_EMIT_WARPS * 32, 0, st>>>((const SplatRec*)packed_params, offset, order, n_capacity,
-                                                                                          cap, img_h, img_w, gx, gy, (unsigned short*)keys, vals, n_dev);)
+                                                                                          cap, img_h, img_w, gx, gy, (unsigned short*)keys, vals, n_dev, valid_pairs);)
     } else {
         LGS_DISPATCH_TILE(tile_h, tile_w,
             emit_pairs_rec_kernel<TH, TW, int><<<grid, LGS_EMIT_WARPS * 32, 0, st>>>((const SplatRec*)packed_params, offset, order, n_capacity, cap,
-                                                                               img_h, img_w, gx, gy, (int*)keys, vals, n_dev);)
+                                                                               img_h, img_w, gx, gy, (int*)keys, vals, n_dev, valid_pairs);)
     }
     LGS_CHECK_LAUNCH("emit_pairs_rec_kernel(dev)");
     return LGS_OK;

@@ -334,7 +334,7 @@ class ViewWorkspace:
         offsets = self.dkey_s           # the sorted keys are dead: their storage receives the scan
         _lib.call("lgs_scan_gathered_dev", _ptr(self.tcount), _ptr(self.order), N, n_dev, _ptr(offsets), _ptr(self.ws), wsz, st)
         _lib.call("lgs_emit_pairs_dev", _ptr(self.packed), _ptr(offsets), _ptr(self.order), N, n_dev, D, H, W, th, tw, 16 if self.u16 else 32,
-                  _ptr(self.keys), _ptr(self.vals), st)
+                  _ptr(self.keys), _ptr(self.vals), d_dev, st)
         bits = self.ntile.bit_length()
         _lib.call("lgs_sort_pairs_u16_dev" if self.u16 else "lgs_sort_pairs_u32k_dev", _ptr(self.keys), _ptr(self.keys_s), _ptr(self.vals),
                   _ptr(self.sorted_pid), D, d_dev, 0, bits, _ptr(self.ws), wsz, st)
@@ -366,14 +366,15 @@ class ViewWorkspace:
     def _run(self, kind, sig, fn):
         """Eager the first time a pointer signature is seen, captured into a CUDA graph the second time, replayed afterwards."""
         key = (kind, sig)
-        g = self._graphs.get(key)
+        graphs = self.use_graphs and GRAPHS_ENABLED          # GRAPHS_ENABLED: module-wide switch (stage timing, A/B)
+        g = self._graphs.get(key) if graphs else None
         if g is not None:
             g.replay()
             return
         seen = self._eager_runs.get(key, 0)
         cur = torch.cuda.current_stream(self.dev)
-        # graphs cannot be captured on the legacy default stream; GRAPHS_ENABLED is the module-wide switch (stage timing, A/B)
-        if not (self.use_graphs and GRAPHS_ENABLED) or seen < 1 or cur.cuda_stream == 0:
+        # graphs cannot be captured on the legacy default stream
+        if not graphs or seen < 1 or cur.cuda_stream == 0:
             self._eager_runs[key] = seen + 1
             fn()
             return
