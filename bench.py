@@ -589,11 +589,21 @@ def run_ours(args, rank, world, local_rank):
         loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
         pending = {"k": None}
 
-        def e2e_camera(j):          # H2D of the view's camera, on the view's stream
-            return {k: v.to(dev, non_blocking=True) for k, v in cam_host[j].items()}
+        copy_stream = torch.cuda.Stream(device=dev)
+        gt_inflight = {}
 
-        def e2e_loss(j, img):       # H2D of the uint8 target, loss, D2H of the result
-            gt = gt_host[j % 2].to(dev, non_blocking=True)
+        def e2e_camera(j):          # H2D of the view's camera on the view's stream; the target image is prefetched on a copy stream
+            cam = {k: v.to(dev, non_blocking=True) for k, v in cam_host[j].items()}
+            with torch.cuda.stream(copy_stream):
+                gt = gt_host[j % 2].to(dev, non_blocking=True)
+                ev = torch.cuda.Event(); ev.record(copy_stream)
+            gt_inflight[j] = (gt, ev)
+            return cam
+
+        def e2e_loss(j, img):       # (H2D of the uint8 target was started before the view's forward), loss, D2H of the result
+            gt, ev = gt_inflight.pop(j)
+            torch.cuda.current_stream(dev).wait_event(ev)
+            gt.record_stream(torch.cuda.current_stream(dev))
             # loss = sum(img * (gt/255 - 0.5)) and its gradient (gt - 127.5)/255, handed to the rasterizer directly
             # (render_views' loss-and-gradient form): two elementwise kernels and one dot product per view
             d_img = torch.sub(gt, 127.5).mul_(1.0 / 255.0)
@@ -645,7 +655,8 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         e2e = {"value": vpr * world * n_e2e / (float(t2.item()) / 1000.0), "unit": UNIT,
                "h2d_bytes_per_step": int(h2d * vpr), "d2h_bytes_per_step": int(4 * vpr),
-               "note": "per view: pinned camera + uint8 target H2D on the view's stream, loss D2H into pinned memory; the host reads "
+               "note": "per view: pinned camera H2D on the view's stream, uint8 target H2D on a copy stream started before the view's forward, "
+                       "loss + dL/dimg from the target (render_views' loss-and-gradient form), loss D2H into pinned memory; the host reads "
                        "each step's losses after enqueuing the next step (every step's result is read inside the timed region)"}
 
     if rank != 0:

@@ -65,10 +65,18 @@ def load_dataset(root, image_dir="images", dev=None):
 
 
 def train(root, iters=300, views_per_step=8, log=print):
+    from litegs_b200 import fused
+    keep = fused.CONFIG["true_sigmoid_grad"]
+    fused.CONFIG["true_sigmoid_grad"] = True               # our own loops train with the true sigmoid derivative (SURVEY Q15)
+    try:
+        return _train(root, iters, views_per_step, log)
+    finally:
+        fused.CONFIG["true_sigmoid_grad"] = keep
+
+
+def _train(root, iters, views_per_step, log):
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
     torch.cuda.set_device(dev)
-    from litegs_b200 import fused
-    fused.CONFIG["true_sigmoid_grad"] = True               # our own loops train with the true sigmoid derivative (SURVEY Q15)
     frames, xyz, rgb = load_dataset(root, dev=dev)
     H, W = frames[0][2]
     g = colmap.gaussians_from_points(xyz, rgb, sh_degree=3)

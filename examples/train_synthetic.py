@@ -24,6 +24,15 @@ from litegs_b200.dist import PARAM_ORDER  # noqa: E402
 
 def train(n_gaussians=50_000, hw=(270, 480), n_views=16, iters=100, seed=0, device=None, log=print, perturb=0.3):
     """Returns the list of per-iteration mean losses (rank-local views)."""
+    keep = fused.CONFIG["true_sigmoid_grad"]
+    fused.CONFIG["true_sigmoid_grad"] = True               # our own loops train with the true sigmoid derivative (SURVEY Q15)
+    try:
+        return _train(n_gaussians, hw, n_views, iters, seed, device, log, perturb)
+    finally:
+        fused.CONFIG["true_sigmoid_grad"] = keep
+
+
+def _train(n_gaussians, hw, n_views, iters, seed, device, log, perturb):
     import torch.distributed as dist
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
@@ -36,7 +45,6 @@ def train(n_gaussians=50_000, hw=(270, 480), n_views=16, iters=100, seed=0, devi
     A = [torch.from_numpy(truth[k]).to(dev) for k in ("cluster_origin", "cluster_extend")]
     cams = [{k: torch.from_numpy(v).to(dev) for k, v in scene.make_camera(j, n_views, W, H).items()} for j in range(n_views)]
     mine = lgs_dist.shard_views(n_views, rank, world)      # shards may differ by one view: the loss is the mean over ALL n_views
-    fused.CONFIG["true_sigmoid_grad"] = True               # our own loops train with the true sigmoid derivative
     with torch.no_grad():       # targets: renders of the true scene
         gts = {j: render.render_view(A[0], A[1], cams[j]["frustumplane"], cams[j]["view"], cams[j]["proj"], T["xyz"], T["scale"], T["rot"],
                                      T["sh_0"], T["sh_rest"], T["opacity"], 3, (H, W), pp)[0].contiguous() for j in mine}

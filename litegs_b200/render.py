@@ -340,10 +340,10 @@ class _ViewSlots:
         self.cap, self.bits = 0, 24
 
     def size(self, max_pairs, max_bits):
-        """Capacities from the measured maxima: 30 % head-room on the pairs, the depth range rounded up to whole 8-bit passes with
-        at least one spare bit."""
+        """Capacities from the measured maxima: 30 % head-room on the pairs, the depth range rounded up to whole 8-bit passes (a
+        view that needs more is flagged and the step redone)."""
         self.cap = int(max_pairs * 1.3) + 65536
-        self.bits = min(32, 8 * ((max_bits + 1 + 7) // 8))
+        self.bits = min(32, 8 * ((max_bits + 7) // 8))
         self.ws = []
 
     def ensure(self, n_slots):
