@@ -293,9 +293,22 @@ int lgs_adam_step_dense(float* const* params, const int* rows_per_param, const f
                         float* exp_avg, float* exp_avg_sq, float* touched, int C, int S, double b1, double b2, double eps,
                         int clear_grad, void* stream);
 
-/* gpu_driven_pipeline_sparse_op, GR/compact.cu:1221-1336 (GR/compact.h:30-36). dtype 0=f32 1=i32; op 0=add 1=min 2=max */
+/* gpu_driven_pipeline_sparse_op, GR/compact.cu:1221-1336 (GR/compact.h:30-36).  dtype 0=f32 1=i32 2=f64 3=i64 4=i16 5=i8 6=u8
+ * (the reference dispatches AT_DISPATCH_ALL_TYPES, :1305); op 0=add 1=min 2=max */
 int lgs_sparse_chunk_op(void* A, const void* B, const int64_t* visible_chunk_ids, const int* visible_count, int dtype,
                         int op, int ele_num, int chunks, int alloc_chunks, int chunk_size, void* stream);
+
+/* ---- chunk maintenance between epochs ----------------------------------------------------------------- */
+
+/* Morton codes of _gen_morton_code (litegs/scene/point.py:38-81): xyz f32[3,N], lo3/hi3 DEVICE f32[3] (per-axis min / max),
+ * bits per axis (the reference uses 21) -> codes i64[N].  spatial_refine (point.py:85-154) = stable sort of these codes. */
+int lgs_morton_codes(const float* xyz, const float* lo3, const float* hi3, int N, int bits, long long* codes, void* stream);
+/* dst[r, j] = src[r, idx[j]], all R rows of a [R,N] matrix in one launch (parameters / gradients / Adam moments reordered
+ * by the sorted Morton order, point.py:104-140). */
+int lgs_permute_rows(const float* src, const long long* idx, int R, int N, float* dst, void* stream);
+/* get_cluster_AABB (litegs/scene/cluster.py:29-46) from the RAW clustered parameters xyz/scale f32[3,C,S], rot f32[4,C,S]
+ * -> origin, extend f32[3,C]. */
+int lgs_cluster_aabb(const float* xyz, const float* scale, const float* rot, int C, int S, float* origin, float* extend, void* stream);
 
 /* ---- fused SSIM / L1 + SSIM loss (next row; what trainer.py:145 calls) ------------------ */
 

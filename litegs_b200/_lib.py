@@ -70,6 +70,9 @@ SIGNATURES = {
     "lgs_adam_update_primitive": [_P, _P, _P, _P, _P, _I, _I, _D, _D, _D, _D, _P],
     "lgs_sparse_chunk_op": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "lgs_mark_visible_chunks": [_P, _P, _I, _P, _P],
+    "lgs_morton_codes": [_P, _P, _P, _I, _I, _P, _P],
+    "lgs_permute_rows": [_P, _P, _I, _I, _P, _P],
+    "lgs_cluster_aabb": [_P, _P, _P, _I, _I, _P, _P, _P],
     "lgs_adam_step_dense": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _D, _D, _D, _I, _P],
     "lgs_ssim_num_block_sums": [_I, _I, _I, _I, ctypes.POINTER(_I)],
     "lgs_ssim_forward": [_P, _P, _I, _I, _I, _I, _F, _F, _I, _F, _P, _P, _P, _P, _P, _P],

@@ -769,19 +769,29 @@ __global__ void sparse_scatter_kernel(T* __restrict__ A, const T* __restrict__ B
     else A[oa] = max(A[oa], b);
 }
 
-// dtype: 0 = float32, 1 = int32 ; op: 0 add, 1 min, 2 max
+// dtype: 0 float32, 1 int32, 2 float64, 3 int64, 4 int16, 5 int8, 6 uint8 (the reference dispatches AT_DISPATCH_ALL_TYPES,
+// GR/compact.cu:1305); op: 0 add, 1 min, 2 max
 extern "C" int lgs_sparse_chunk_op(void* A, const void* B, const int64_t* visible_chunk_ids, const int* visible_count, int dtype,
                                    int op, int ele_num, int chunks, int alloc_chunks, int chunk_size, void* stream)
 {
     LGS_REQUIRE(chunk_size >= 1 && chunk_size <= 1024, "gpu_driven_pipeline_sparse_op: chunk_size %d exceeds max threads per block", chunk_size);
     LGS_REQUIRE(op >= 0 && op <= 2, "gpu_driven_pipeline_sparse_op: unsupported op %d (expected add, min, max)", op);
-    LGS_REQUIRE(dtype == 0 || dtype == 1, "gpu_driven_pipeline_sparse_op: unsupported dtype code %d", dtype);
+    LGS_REQUIRE(dtype >= 0 && dtype <= 6, "gpu_driven_pipeline_sparse_op: unsupported dtype code %d", dtype);
     if (alloc_chunks == 0 || ele_num == 0) return LGS_OK;
     dim3 grid(alloc_chunks, ele_num);
     cudaStream_t st = (cudaStream_t)stream;
 #define SC(T, OP) sparse_scatter_kernel<T, OP><<<grid, chunk_size, 0, st>>>((T*)A, (const T*)B, visible_chunk_ids, visible_count, chunks, alloc_chunks)
-    if (dtype == 0) { if (op == 0) SC(float, 0); else if (op == 1) SC(float, 1); else SC(float, 2); }
-    else { if (op == 0) SC(int, 0); else if (op == 1) SC(int, 1); else SC(int, 2); }
+#define SCT(T) do { if (op == 0) SC(T, 0); else if (op == 1) SC(T, 1); else SC(T, 2); } while (0)
+    switch (dtype) {
+        case 0: SCT(float); break;
+        case 1: SCT(int); break;
+        case 2: SCT(double); break;
+        case 3: SCT(long long); break;
+        case 4: SCT(short); break;
+        case 5: SCT(signed char); break;
+        default: SCT(unsigned char); break;
+    }
+#undef SCT
 #undef SC
     LGS_CHECK_LAUNCH("sparse_scatter_kernel");
     return LGS_OK;

@@ -492,8 +492,9 @@ def gpu_driven_pipeline_sparse_op(A, B, visible_chunk_ids, visible_count, op_nam
     ops = {"add": 0, "sum": 0, "min": 1, "max": 2}
     if op_name not in ops:
         raise RuntimeError(f"Unsupported op: {op_name}. Expected: add, min, max")
-    if A.dtype != B.dtype or A.dtype not in (_F32, _I32):
-        raise RuntimeError(f"gpu_driven_pipeline_sparse_op: dtype {A.dtype}/{B.dtype} unsupported (float32, int32)")
+    codes = {_F32: 0, _I32: 1, torch.float64: 2, _I64: 3, torch.int16: 4, torch.int8: 5, torch.uint8: 6}     # AT_DISPATCH_ALL_TYPES
+    if A.dtype != B.dtype or A.dtype not in codes:
+        raise RuntimeError(f"gpu_driven_pipeline_sparse_op: dtype {A.dtype}/{B.dtype} unsupported (expected one of {list(codes)})")
     if not A.is_contiguous():
         raise RuntimeError("gpu_driven_pipeline_sparse_op: A must be contiguous (updated in place)")
     Bc = B if B.is_contiguous() else B.contiguous()
@@ -503,7 +504,7 @@ def gpu_driven_pipeline_sparse_op(A, B, visible_chunk_ids, visible_count, op_nam
         raise RuntimeError("chunk_size exceeds max threads per block")
     dev = A.device
     with torch.cuda.device(dev):
-        _lib.call("lgs_sparse_chunk_op", _ptr(A), _ptr(Bc), _ptr(ids), _ptr(cnt), 0 if A.dtype == _F32 else 1, ops[op_name], E, C,
+        _lib.call("lgs_sparse_chunk_op", _ptr(A), _ptr(Bc), _ptr(ids), _ptr(cnt), codes[A.dtype], ops[op_name], E, C,
                   Bc.shape[1], S, _stream(dev))
 
 

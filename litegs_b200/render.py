@@ -106,6 +106,27 @@ def render(view_matrix, proj_matrix, xyz, scale, rot, color, opacity,
 # Level B: one differentiable call per view
 # ---------------------------------------------------------------------------------------------------
 
+@torch.no_grad()
+def _feed_statistics(state, stats, packed_grad, tile):
+    """What Level A feeds the StatisticsHelper op by op (render/__init__.py:24-25,84-85; wrapper.py:501-506,733-737), from the
+    fused pipeline's state: compact mask + device-side visible count, visible splats, fragment weight / count, fragment error
+    (d_opacity = sum s0 / o and the err_square term of the gradient record), per-tile blend counts."""
+    SH = StatisticsHelperInst
+    if SH.on_compact_mask is not None:
+        SH.on_compact_mask(state.chunk_ids, state.counters[:1])
+    if SH.on_visible is not None:
+        SH.on_visible((state.tile_count > 0).reshape(1, -1))
+    fc, fw = stats
+    if SH.on_fragment_weight is not None:
+        SH.on_fragment_weight(fw, fc)
+    if SH.on_fragment_err is not None and packed_grad is not None:
+        o = state.packed[..., 5]
+        d_op = torch.where(o > 0, packed_grad[..., 8] / o.clamp_min(1e-30), torch.zeros_like(o))
+        SH.on_fragment_err(d_op.unsqueeze(0), packed_grad[..., 9].unsqueeze(0), fc)
+    if SH.on_blend_count is not None:
+        SH.on_blend_count(state.last, tile[0], tile[1])
+
+
 class _RenderViewFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xyz, scale, rot, sh_0, sh_rest, opacity, cluster_origin, cluster_extend, frustumplane,
@@ -137,8 +158,8 @@ class _RenderViewFn(torch.autograd.Function):
         grads, pg = pipeline.render_view_backward(params, state, g_img, g_T if (ctx.trans and g_T is not None) else None,
                                                   enable_statistic=ctx.stat,
                                                   accumulate_into=ctx.accumulate_into, clamped_img=img_out)
-        if ctx.stat and StatisticsHelperInst.on_fragment_weight is not None:
-            StatisticsHelperInst.on_fragment_weight(ctx.stats[1], ctx.stats[0])
+        if ctx.stat:
+            _feed_statistics(state, ctx.stats, pg, state.tile)
         if grads is None:          # gradients went straight into the caller's dense buffers
             ctx.state = None
             return (None,) * 19
@@ -236,9 +257,10 @@ def render_views(n_views: int, camera_fn, loss_fn, cluster_origin, cluster_exten
             d_img = torch.nn.functional.pad(d_img, (0, img_p.shape[-1] - W, 0, img_p.shape[-2] - H))
         if wait_ev is not None:
             torch.cuda.current_stream(dev).wait_event(wait_ev)
-        pipeline.render_view_backward(params, state, d_img, None, enable_statistic=stat, accumulate_into=accumulate_into, clamped_img=img_p)
-        if stat and StatisticsHelperInst.on_fragment_weight is not None:
-            StatisticsHelperInst.on_fragment_weight(stats[1], stats[0])
+        _, pg_ = pipeline.render_view_backward(params, state, d_img, None, enable_statistic=stat, accumulate_into=accumulate_into,
+                                               clamped_img=img_p)
+        if stat:
+            _feed_statistics(state, stats, pg_, (th, tw))
         losses.append(loss.detach())
 
     def one_autograd(i, wait_ev):

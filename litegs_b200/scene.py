@@ -162,3 +162,66 @@ def make_scene(n: int, sh_degree: int = 3, chunk: int = 128, seed: int = 0, log_
     p["cluster_extend"] = extend
     p["n_points"] = n
     return p
+
+
+# ---------------------------------------------------------------------------------------------------
+# chunk maintenance on the device: Morton re-clustering and chunk AABBs as single kernels
+# ---------------------------------------------------------------------------------------------------
+
+def cluster_aabb_device(xyz_c, scale_c, rot_c):
+    """get_cluster_AABB (litegs/scene/cluster.py:29-46) in one kernel (csrc/scene.cu) from the RAW clustered parameters
+    xyz/scale [3,C,S], rot [4,C,S] (float32 CUDA) -> (origin [3,C], extend [3,C])."""
+    import torch
+    from . import _lib
+    from .fused import _f32c, _ptr, _stream
+    x, s, q = _f32c(xyz_c.detach(), "xyz"), _f32c(scale_c.detach(), "scale"), _f32c(rot_c.detach(), "rot")
+    C, S = x.shape[-2:]
+    dev = x.device
+    with torch.cuda.device(dev):
+        origin = torch.empty((3, C), dtype=torch.float32, device=dev)
+        extend = torch.empty((3, C), dtype=torch.float32, device=dev)
+        _lib.call("lgs_cluster_aabb", _ptr(x), _ptr(s), _ptr(q), C, S, _ptr(origin), _ptr(extend), _stream(dev))
+    return origin, extend
+
+
+def morton_codes_device(xyz, bits: int = 21):
+    """_gen_morton_code (litegs/scene/point.py:38-81) for xyz f32[3,N] on CUDA -> int64[N]."""
+    import torch
+    from . import _lib
+    from .fused import _f32c, _ptr, _stream
+    p = _f32c(xyz.detach(), "xyz")
+    if p.dim() != 2 or p.shape[0] != 3:
+        raise RuntimeError("positions must be a (3, N) tensor")
+    dev, N = p.device, p.shape[1]
+    with torch.cuda.device(dev):
+        lo = p.amin(dim=1).contiguous()
+        hi = p.amax(dim=1).contiguous()
+        codes = torch.empty(N, dtype=torch.int64, device=dev)
+        _lib.call("lgs_morton_codes", _ptr(p), _ptr(lo), _ptr(hi), N, int(bits), _ptr(codes), _stream(dev))
+    return codes
+
+
+def spatial_refine_device(tensors: dict, xyz_key: str = "xyz"):
+    """spatial_refine (litegs/scene/point.py:85-154) for clustered tensors: every entry of `tensors` is [..., C, S] float32 CUDA
+    (parameters, their gradients, Adam moments ...); all are re-ordered by the stable Morton order of tensors[xyz_key] and
+    re-clustered.  Returns (dict of new tensors, the permutation int64[C*S]).  Each tensor is permuted by ONE launch."""
+    import torch
+    from . import _lib
+    from .fused import _f32c, _ptr, _stream
+    xyz = tensors[xyz_key]
+    C, S = xyz.shape[-2:]
+    N = C * S
+    dev = xyz.device
+    codes = morton_codes_device(xyz.detach().reshape(3, N))
+    _, order = codes.sort(stable=True)                                     # point.py:92 (torch.sort: integer keys, exact)
+    out = {}
+    with torch.cuda.device(dev):
+        for k, t in tensors.items():
+            src = _f32c(t.detach(), k)
+            if tuple(src.shape[-2:]) != (C, S):
+                raise RuntimeError(f"spatial_refine_device: '{k}' is not clustered like '{xyz_key}'")
+            R = src.numel() // N
+            dst = torch.empty_like(src)
+            _lib.call("lgs_permute_rows", _ptr(src), _ptr(order), R, N, _ptr(dst), _stream(dev))
+            out[k] = dst
+    return out, order
