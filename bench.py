@@ -589,24 +589,32 @@ def run_ours(args, rank, world, local_rank):
         loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
         pending = {"k": None}
 
+        # target images: a fixed device buffer per view of the step, filled from pinned memory on a copy stream BEFORE the view's
+        # forward is enqueued (no allocation inside the loop, the copy overlaps the view's own kernels)
         copy_stream = torch.cuda.Stream(device=dev)
-        gt_inflight = {}
+        gt_dev = [torch.empty((1, 3, H, W), dtype=torch.uint8, device=dev) for _ in range(vpr)]
+        gt_ready = [None] * vpr
+        gt_consumed = [None] * vpr
 
-        def e2e_camera(j):          # H2D of the view's camera on the view's stream; the target image is prefetched on a copy stream
+        def e2e_camera(j):          # H2D of the view's camera on the view's stream; the target image is prefetched on the copy stream
             cam = {k: v.to(dev, non_blocking=True) for k, v in cam_host[j].items()}
+            if gt_consumed[j] is not None:
+                copy_stream.wait_event(gt_consumed[j])       # last step's loss of this slot has read the buffer
             with torch.cuda.stream(copy_stream):
-                gt = gt_host[j % 2].to(dev, non_blocking=True)
+                gt_dev[j].copy_(gt_host[j % 2], non_blocking=True)
                 ev = torch.cuda.Event(); ev.record(copy_stream)
-            gt_inflight[j] = (gt, ev)
+            gt_ready[j] = ev
             return cam
 
         def e2e_loss(j, img):       # (H2D of the uint8 target was started before the view's forward), loss, D2H of the result
-            gt, ev = gt_inflight.pop(j)
-            torch.cuda.current_stream(dev).wait_event(ev)
-            gt.record_stream(torch.cuda.current_stream(dev))
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(gt_ready[j])
+            gt = gt_dev[j]
             # loss = sum(img * (gt/255 - 0.5)) and its gradient (gt - 127.5)/255, handed to the rasterizer directly
             # (render_views' loss-and-gradient form): two elementwise kernels and one dot product per view
             d_img = torch.sub(gt, 127.5).mul_(1.0 / 255.0)
+            ev = torch.cuda.Event(); ev.record(cur)
+            gt_consumed[j] = ev
             if img is None:
                 return d_img
             loss = torch.dot(img.reshape(-1), d_img.reshape(-1))

@@ -77,11 +77,21 @@ def test_morton_codes_and_spatial_refine(cuda):
         src = T[k].cpu().numpy().reshape(-1, C * S)
         assert np.array_equal(out[k].cpu().numpy().reshape(-1, C * S), src[:, order_np]), k
     ref = _reference_scene_module()
-    if ref is not None:                                             # the reference's own spatial_refine (tensor form, point.py:94-103)
-        r = ref.spatial_refine(True, None, T["xyz"], *[T[k] for k in PARAM_KEYS[1:]])
+    if ref is not None:
+        # the reference's own spatial_refine in its optimizer form (point.py:104-154: parameters and Adam moments reordered in
+        # place; its tensor form, :94-103, passes a tuple to uncluster and cannot run) and its Morton codes
+        prm = {k: torch.nn.Parameter(T[k].clone()) for k in PARAM_KEYS}
+        opt = torch.optim.Adam([{"params": [prm[k]], "lr": 0.0, "name": k} for k in PARAM_KEYS], lr=0.0, eps=1e-15)
+        for k in PARAM_KEYS:
+            opt.state[prm[k]] = {"step": torch.tensor(0.0), "exp_avg": (T[k] * 0.5).clone(), "exp_avg_sq": (T[k] * T[k]).clone()}
+        r = ref.spatial_refine(True, opt, prm["xyz"])
+        mom, _ = scene.spatial_refine_device({"xyz": T["xyz"], **{f"m_{k}": T[k] * 0.5 for k in PARAM_KEYS}, **{f"v_{k}": T[k] * T[k] for k in PARAM_KEYS}})
         for k, t in zip(PARAM_KEYS, r):
-            assert torch.equal(t.reshape(out[k].shape), out[k]), k
-        assert torch.equal(ref.point._gen_morton_code(T["xyz"].reshape(3, -1)), torch.from_numpy(codes).to(cuda))
+            assert torch.equal(t.detach().reshape(out[k].shape), out[k]), k
+            assert torch.equal(opt.state[prm[k]]["exp_avg"].reshape(out[k].shape), mom[f"m_{k}"]), k
+            assert torch.equal(opt.state[prm[k]]["exp_avg_sq"].reshape(out[k].shape), mom[f"v_{k}"]), k
+        import litegs.scene.point as refpoint
+        assert torch.equal(refpoint._gen_morton_code(T["xyz"].reshape(3, -1)), torch.from_numpy(codes).to(cuda))
 
 
 def test_cluster_aabb_device(cuda):
