@@ -229,6 +229,10 @@ int lgs_set_backward_reduce(int deferred);
 int lgs_set_warps_per_block(int wpb);
 /* backward kernel: 2 = packed-pair (fma.rn.f32x2), branch-free pixel body (default); 1 = scalar kernel.  env LGS_BWD=v1|v2 */
 int lgs_set_backward_kernel(int version);
+/* 1 = deterministic backward: per-(tile, splat) sums accumulated as 64-bit fixed point with integer atomics (associative, so
+ * two runs give bit-identical gradients; scratch from the stream-ordered allocator); 0 = fp32 RED atomics (default, faster).
+ * env LGS_DETERMINISTIC=1 */
+int lgs_set_deterministic(int on);
 /* err_square_sum under enable_statistic: 1 = the reference's lane-running recurrence (GR/raster.cu:779-784, default),
  * 0 = sum over pixels of (G dalpha)^2 */
 int lgs_set_err_square_mode(int mode);

@@ -545,7 +545,12 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_kernel(
 // odd rows is squared and added), 0 = sum over pixels of (G dalpha)^2.
 __device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
 
-template <int TH, int TW, bool STAT, bool TRANS>
+// DET (deterministic mode, lgs_set_deterministic): the per-(tile, splat) sums -- themselves computed in a fixed order inside the
+// warp -- are accumulated as 64-bit FIXED-POINT integers (scale 2^36) with integer atomics, which are associative: the result no
+// longer depends on the order in which tiles reach a splat, so two runs give bit-identical gradients (SURVEY 7 asks for such a
+// mode next to the fp32 RED default, whose run-to-run spread is ~1e-6 relative).  `grad` then points at i64[N][LGS_GRAD_FLOATS].
+#define LGS_DET_SCALE 68719476736.0                      // 2^36: |value| < 1.3e8, resolution 1.5e-11
+template <int TH, int TW, bool STAT, bool TRANS, bool DET = false>
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_v2_kernel(
     const int* __restrict__ sorted, const int* __restrict__ start_index, const SplatRec* __restrict__ recs,
     const int* __restrict__ tiles, int n_sel, const float* __restrict__ Tfinal, const unsigned short* __restrict__ last,
@@ -569,7 +574,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_v2_kerne
     const int start = rg[tile_id];
     if (start < 0) return;
     recs += (size_t)b * N;
-    grad += (size_t)b * N * LGS_GRAD_FLOATS;
+    grad += (size_t)b * N * LGS_GRAD_FLOATS * (DET ? 2 : 1);          // DET: 64-bit slots
     const int* ids = sorted + (size_t)b * cap + start;
 
     const int x = ((tile_id - 1) % gx) * TW + lane % TW;
@@ -621,7 +626,12 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_v2_kerne
             const float sum = p0.x + p0.y;
             const int sp = lane / NV, v = lane - sp * NV;
             const int pid = sp == 0 ? pid0 : (sp == 1 ? pid1 : pid2);
-            atomicAdd(&grad[(size_t)pid * LGS_GRAD_FLOATS + v], sum);                            // RED.ADD.F32
+            if (DET) {
+                unsigned long long* gq = reinterpret_cast<unsigned long long*>(grad);
+                atomicAdd(&gq[(size_t)pid * LGS_GRAD_FLOATS + v], (unsigned long long)__double2ll_rn((double)sum * LGS_DET_SCALE));
+            } else {
+                atomicAdd(&grad[(size_t)pid * LGS_GRAD_FLOATS + v], sum);                        // RED.ADD.F32
+            }
         }
         __syncwarp();
         pend = 0;
@@ -727,6 +737,13 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_v2_kerne
     }
     if (pend > 0) flush();
     st.drain();
+}
+
+// deterministic mode: 64-bit fixed point -> the fp32 gradient record
+__global__ void det_to_float_kernel(const long long* __restrict__ q, float* __restrict__ g, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) g[i] = (float)((double)q[i] * (1.0 / LGS_DET_SCALE));
 }
 
 // ---- unpack ----------------------------------------------------------------------------------------
@@ -854,6 +871,19 @@ extern "C" int lgs_set_err_square_mode(int mode)
     return LGS_OK;
 }
 
+// 1 = deterministic backward accumulation (64-bit fixed point, bit-identical run to run; a scratch buffer is taken from the
+// stream-ordered allocator), 0 = fp32 RED atomics (default).  env LGS_DETERMINISTIC=1
+static int g_det = -1;
+static bool deterministic()
+{
+    if (g_det < 0) {
+        const char* e = getenv("LGS_DETERMINISTIC");
+        g_det = (e && e[0] == '1') ? 1 : 0;
+    }
+    return g_det == 1;
+}
+extern "C" int lgs_set_deterministic(int on) { g_det = on ? 1 : 0; return LGS_OK; }
+
 // warps (= tiles) per CTA for the raster kernels: 1, 2 or 4.  Warps of a CTA are independent (no block-level
 // synchronisation), so this only trades CTA-retirement granularity against launch overhead.
 static int g_wpb = -1;
@@ -938,7 +968,23 @@ extern "C" int lgs_rasterize_backward(const int* sorted_points, const int* start
         const bool trans = d_trans_img != nullptr;
         const bool defer = use_deferred_reduce() && !bulk;
         const unsigned short* lastu = (const unsigned short*)last_contributor;
-        if (backward_version() == 2 && !bulk) {
+        if (deterministic()) {
+            // integer accumulation in a stream-ordered scratch buffer, converted into packed_grad afterwards
+            const size_t nq = (size_t)V * N * LGS_GRAD_FLOATS;
+            long long* q = nullptr;
+            LGS_CUDA(cudaMallocAsync((void**)&q, nq * sizeof(long long), st));
+            LGS_CUDA(cudaMemsetAsync(q, 0, nq * sizeof(long long), st));
+#define BWD_DET(S, T) raster_backward_v2_kernel<TH, TW, S, T, true><<<grid, block, 0, st>>>(sorted_points, start_index, recs, specific_tiles, \
+        n_specific, final_transmittance, lastu, d_img, d_trans_img, clamped_img, (float*)q, gx, ntile, cap, N, Hp, Wp, g_err_mode)
+            LGS_DISPATCH_TILE(tile_h, tile_w,
+                if (enable_statistic) { if (trans) BWD_DET(true, true); else BWD_DET(true, false); }
+                else { if (trans) BWD_DET(false, true); else BWD_DET(false, false); })
+#undef BWD_DET
+            LGS_CHECK_LAUNCH("raster_backward_v2_kernel<DET>");
+            det_to_float_kernel<<<lgs_cdiv((long long)nq, 256), 256, 0, st>>>(q, packed_grad, nq);
+            LGS_CHECK_LAUNCH("det_to_float_kernel");
+            LGS_CUDA(cudaFreeAsync(q, st));
+        } else if (backward_version() == 2 && !bulk) {
 #define BW2(S, T) raster_backward_v2_kernel<TH, TW, S, T><<<grid, block, 0, st>>>(sorted_points, start_index, recs, specific_tiles, n_specific, \
         final_transmittance, lastu, d_img, d_trans_img, clamped_img, packed_grad, gx, ntile, cap, N, Hp, Wp, g_err_mode)
             LGS_DISPATCH_TILE(tile_h, tile_w,

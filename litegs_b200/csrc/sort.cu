@@ -27,14 +27,26 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_MAXBINS = 256;          // == RS_THREADS: thread t owns digit t in the block-wide steps
 
 int g_sort_impl = -1;                    // -1: read LGS_SORT on first use; 0 cub; 1 lgs
+bool g_sort_forced = false;              // LGS_SORT / lgs_set_sort_impl given: no automatic choice
 
 int sort_impl()
 {
     if (g_sort_impl < 0) {
         const char* e = getenv("LGS_SORT");
+        g_sort_forced = e != nullptr;
         g_sort_impl = (e != nullptr && strcmp(e, "cub") == 0) ? 0 : 1;
     }
     return g_sort_impl;
+}
+
+// Automatic choice when nothing is forced: the own passes win up to 7-bit digits (1080p: 14 tile bits = 2 x 7, 163 vs 186 us for
+// 10.9 M pairs), cub's onesweep wins when the tile ids need 8-bit digits on tens of millions of pairs (4K: 16 bits, 71.7 M pairs:
+// 0.90 vs 1.26 ms) -- profiles/microbench/dev_count_bench.py.
+int sort_impl_for(int n, int bits, unsigned bias)
+{
+    int impl = sort_impl();
+    if (!g_sort_forced && impl == 1 && bias == 0u && bits > 14 && n > (8 << 20)) impl = 0;
+    return impl;
 }
 
 __device__ __forceinline__ unsigned lanemask_lt()
@@ -219,7 +231,8 @@ template <typename KeyT>
 RsPlan rs_plan(int n, int begin_bit, int end_bit)
 {
     RsPlan p;
-    p.ipt = n > (1 << 22) ? 16 : 8;
+    static const int forced_ipt = getenv("LGS_RS_IPT") ? atoi(getenv("LGS_RS_IPT")) : 0;      // A/B knob: 8 | 16
+    p.ipt = (forced_ipt == 8 || forced_ipt == 16) ? forced_ipt : (n > (1 << 22) ? 16 : 8);
     p.tile = RS_THREADS * p.ipt;
     p.nblocks = (n + p.tile - 1) / p.tile;
     int bits = end_bit - begin_bit;
@@ -296,7 +309,8 @@ int sort_pairs(const char* who, const KeyT* keys_in, KeyT* keys_out, const unsig
                 end_bit);
     char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     size_t need;
-    if (sort_impl() == 0) {
+    const int impl = sort_impl_for(n, end_bit - begin_bit, bias);
+    if (impl == 0) {
         if (bias != 0u) { begin_bit = 0; end_bit = 8 * (int)sizeof(KeyT); }   // cub cannot rebase: all bits of the raw keys, same order
         need = 0;
         cub::DeviceRadixSort::SortPairs<KeyT, unsigned>(nullptr, need, nullptr, nullptr, nullptr, nullptr, n, begin_bit, end_bit);
@@ -307,7 +321,7 @@ int sort_pairs(const char* who, const KeyT* keys_in, KeyT* keys_out, const unsig
         lgs_set_error("%s: workspace of %zu bytes needed, %zu given", who, need + 256, workspace_bytes);
         return LGS_ERR_WORKSPACE;
     }
-    if (sort_impl() == 0) {
+    if (impl == 0) {
         LGS_CUDA(cub::DeviceRadixSort::SortPairs<KeyT, unsigned>(ws, need, keys_in, keys_out, vals_in, vals_out, n, begin_bit, end_bit,
                                                                  (cudaStream_t)stream));
         return LGS_OK;
@@ -322,6 +336,7 @@ extern "C" int lgs_set_sort_impl(int impl)
 {
     LGS_REQUIRE(impl == 0 || impl == 1, "set_sort_impl: %d is not 0 (cub) or 1 (lgs)", impl);
     g_sort_impl = impl;
+    g_sort_forced = true;
     return LGS_OK;
 }
 

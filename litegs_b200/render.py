@@ -283,6 +283,8 @@ def render_views(n_views: int, camera_fn, loss_fn, cluster_origin, cluster_exten
     slots = None
     if direct and pipeline.SYNC_FREE and not stat:
         slots = _view_slots(params, (H, W), (th, tw), max(1, n_streams))
+        if slots.big:
+            slots = None
     probe = {"pairs": 0, "bits": 1} if (slots is not None and slots.ws is None) else None
 
     def one_ws(i, wait_ev, ws):
@@ -359,6 +361,7 @@ class _ViewSlots:
     def __init__(self, params, hw, tile):
         self.params_like, self.hw, self.tile = params, hw, tile
         self.ws = None
+        self.big = False
         self.cap, self.bits = 0, 24
 
     def size(self, max_pairs, max_bits):
@@ -366,7 +369,12 @@ class _ViewSlots:
         view that needs more is flagged and the step redone)."""
         self.cap = int(max_pairs * 1.3) + 65536
         self.bits = min(32, 8 * ((max_bits + 7) // 8))
-        self.ws = []
+        H, W = self.hw
+        ntile = ((W + self.tile[1] - 1) // self.tile[1]) * ((H + self.tile[0] - 1) // self.tile[0])
+        # very large pair lists with 8-bit tile digits (4K frames): the library's onesweep, which needs the count on the host,
+        # beats the own passes (csrc/sort.cu: sort_impl_for) and such views are device-bound anyway -> stay on the synchronising path
+        self.ws = None if (ntile.bit_length() > 14 and max_pairs > (8 << 20)) else []
+        self.big = self.ws is None
 
     def ensure(self, n_slots):
         """One workspace per stream slot (created on demand once the capacities are known)."""

@@ -396,3 +396,45 @@ def test_last_contributor_is_unsigned_16_bit(cuda):
         assert abs(float(got[3][0, -1])) > 0
         for a, b, name in zip(got[:4], ref[:4], ("d_ndc", "d_cov2d_inv", "d_color", "d_opacity")):
             assert scaled_err(a.cpu().numpy(), b) < 2e-4, (bwd, name, scaled_err(a.cpu().numpy(), b))
+
+
+def test_deterministic_backward_is_bit_identical(cuda, proj):
+    """lgs_set_deterministic(1): the backward accumulates the per-(tile, splat) sums as 64-bit fixed point with integer atomics,
+    so the gradients of two runs are bit-identical (and still match the oracle); the default fp32 RED path is only reproducible to
+    rounding.  Checked on the op level (oracle forward state) and through the fused pipeline with its unordered tile buckets."""
+    o, hw = proj["o"], proj["hw"]
+    tile = (8, 16)
+    th, tw = tile
+    ranges, pid, oT, olast, g, _, _ = _backward_inputs(proj, tile, seed=9)
+    gmax = float(np.abs(g).max())
+    ref = oracle.rasterize_backward(pid, ranges, o["ndc"], o["inv_cov2d"], o["color"], o["opacity"], None, oT, olast, g / gmax, None, gmax,
+                                    hw[0], hw[1], th, tw)
+    packed = fused.rasterize_forward(T(pid, cuda), T(ranges, cuda), T(o["ndc"], cuda), T(o["inv_cov2d"], cuda), T(o["color"], cuda),
+                                     T(o["opacity"], cuda), None, hw[0], hw[1], th, tw, False, False, False)[4]
+
+    def run():
+        return fused.rasterize_backward(T(pid, cuda), T(ranges, cuda), packed, None, T(oT, cuda), T(olast, cuda), T(g / gmax, cuda), None, None,
+                                        torch.tensor([gmax], device=cuda), hw[0], hw[1], th, tw, False)
+    _lib.call("lgs_set_deterministic", 1)
+    try:
+        a, b = run(), run()
+        for x, y, r, name in zip(a[:4], b[:4], ref[:4], ("d_ndc", "d_cov2d_inv", "d_color", "d_opacity")):
+            assert torch.equal(x, y), name
+            assert scaled_err(x.cpu().numpy(), r) < TOL, name
+        # fused pipeline, 4000 Gaussians: forward + backward twice from scratch
+        params, aabb, cam = small_scene(n=4000, hw=hw, tile=tile, seed=11)
+        w = torch.from_numpy(np.random.default_rng(0).normal(size=(1, 3, *hw)).astype(np.float32)).to(cuda)
+        pp = PipelineParams(tile_size=tile)
+        res = []
+        for _ in range(2):
+            P = {k: torch.from_numpy(params[k]).to(cuda).requires_grad_(True) for k in PARAM_KEYS}
+            A = [torch.from_numpy(x).to(cuda) for x in aabb]
+            C = {k: torch.from_numpy(v).to(cuda) for k, v in cam.items()}
+            img = render.render_view(A[0], A[1], C["frustumplane"], C["view"], C["proj"], P["xyz"], P["scale"], P["rot"], P["sh_0"], P["sh_rest"],
+                                     P["opacity"], 3, hw, pp)[0]
+            (img * w).sum().backward()
+            res.append({k: P[k].grad.compacted_values.clone() for k in PARAM_KEYS})
+        for k in PARAM_KEYS:
+            assert torch.equal(res[0][k], res[1][k]), k
+    finally:
+        _lib.call("lgs_set_deterministic", 0)
