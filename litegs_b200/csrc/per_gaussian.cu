@@ -716,12 +716,50 @@ __global__ void adam_chunk_kernel(float* __restrict__ param, const float* __rest
     m[p] = e1; v2[p] = e2;
 }
 
+// Same update with 16-byte accesses: a thread owns 4 consecutive Gaussians of a chunk, a CTA covers ROWS rows of one visible
+// chunk (S/4 x ROWS threads).  Four times fewer threads and four times more bytes in flight per thread than the one-element
+// form (which is what the reference launches: GR/compact.cu:320-344) -- the six launches of an optimiser step are bandwidth
+// bound, not latency bound, this way.
+template <int ROWS>
+__global__ void adam_chunk_vec4_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
+                                       float* __restrict__ v2, const int64_t* __restrict__ ids, const int* __restrict__ valid_length,
+                                       int R, int C, int S, int A, float lr, float b1, float b2, float eps)
+{
+    const int a = blockIdx.x, r = blockIdx.y * ROWS + threadIdx.y;
+    if (r >= R || (valid_length != nullptr && a >= valid_length[0])) return;
+    const size_t p = ((size_t)r * C + ids[a]) * S + 4 * threadIdx.x;
+    const float4 g4 = *reinterpret_cast<const float4*>(grad + ((size_t)r * A + a) * S + 4 * threadIdx.x);
+    float4 m4 = *reinterpret_cast<const float4*>(m + p), v4 = *reinterpret_cast<const float4*>(v2 + p);
+    float4 p4 = *reinterpret_cast<const float4*>(param + p);
+    const float* gp = &g4.x; float* mp = &m4.x; float* vp = &v4.x; float* pq = &p4.x;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float g = gp[i];
+        const float e1 = b1 * mp[i] + (1.0f - b1) * g;
+        const float e2 = b2 * vp[i] + (1.0f - b2) * g * g;
+        pq[i] += -lr * e1 / (sqrtf(e2) + eps);
+        mp[i] = e1; vp[i] = e2;
+    }
+    *reinterpret_cast<float4*>(param + p) = p4;
+    *reinterpret_cast<float4*>(m + p) = m4;
+    *reinterpret_cast<float4*>(v2 + p) = v4;
+}
+
 extern "C" int lgs_adam_update_chunk(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                                      const int64_t* visible_index, const int* valid_length, int R, int C, int S, int A,
                                      double lr, double b1, double b2, double eps, void* stream)
 {
     LGS_REQUIRE(S >= 1 && S <= 1024, "adamUpdate: chunk size %d unsupported", S);
     if (A == 0 || R == 0) return LGS_OK;
+    const bool aligned = ((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0) && S % 4 == 0 &&
+                         S / 4 <= 128;
+    if (aligned) {
+        constexpr int ROWS = 8;
+        adam_chunk_vec4_kernel<ROWS><<<dim3(A, lgs_cdiv(R, ROWS)), dim3(S / 4, ROWS), 0, (cudaStream_t)stream>>>(
+            param, grad, exp_avg, exp_avg_sq, visible_index, valid_length, R, C, S, A, (float)lr, (float)b1, (float)b2, (float)eps);
+        LGS_CHECK_LAUNCH("adam_chunk_vec4_kernel");
+        return LGS_OK;
+    }
     adam_chunk_kernel<<<dim3(A, R), S, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, visible_index, valid_length, C, S, A,
                                                                  (float)lr, (float)b1, (float)b2, (float)eps);
     LGS_CHECK_LAUNCH("adam_chunk_kernel");
