@@ -227,6 +227,8 @@ int lgs_set_staging(int bulk);
 int lgs_set_backward_reduce(int deferred);
 /* tiles (warps) per CTA of the raster kernels: 1, 2 or 4 (default 4, env LGS_WPB) */
 int lgs_set_warps_per_block(int wpb);
+/* forward blend on packed pixel pairs (fma.rn.f32x2): 1 on, 0 = scalar predicated body.  env LGS_FWD_PAIRS=0|1 */
+int lgs_set_forward_pairs(int on);
 /* backward kernel: 2 = packed-pair (fma.rn.f32x2), branch-free pixel body (default); 1 = scalar kernel.  env LGS_BWD=v1|v2 */
 int lgs_set_backward_kernel(int version);
 /* 1 = deterministic backward: per-(tile, splat) sums accumulated as 64-bit fixed point with integer atomics (associative, so

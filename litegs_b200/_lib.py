@@ -61,6 +61,7 @@ SIGNATURES = {
     "lgs_set_warps_per_block": [_I],
     "lgs_set_backward_reduce": [_I],
     "lgs_set_backward_kernel": [_I],
+    "lgs_set_forward_pairs": [_I],
     "lgs_set_err_square_mode": [_I],
     "lgs_set_deterministic": [_I],
     "lgs_project_forward": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],

@@ -194,7 +194,8 @@ __global__ void pack_kernel(const float* __restrict__ ndc, const float* __restri
 }
 
 // ---- forward ---------------------------------------------------------------------------------------
-template <int TH, int TW, bool STAT, bool BULK>
+// PAIRS: blend the lane's pixels two at a time with packed fp32 (A/B switch, lgs_set_forward_pairs / env LGS_FWD_PAIRS).
+template <int TH, int TW, bool STAT, bool BULK, bool PAIRS = false>
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_forward_kernel(
     const int* __restrict__ sorted, const int* __restrict__ start_index, const SplatRec* __restrict__ recs,
     const int* __restrict__ tiles, int n_sel, float* __restrict__ img, float* __restrict__ Tout, unsigned short* __restrict__ last,
@@ -270,6 +271,32 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_forward_kernel(
                 const float base = a2 * dx * dx, lin = b2 * dx;
                 const float os = q1.y * KS;
                 int fcount = 0; float wsum = 0.f;
+                if (PAIRS && !STAT) {
+                    // packed-pair form (fma/mul/add.rn.f32x2): the two pixels of a pair share every instruction of the chain;
+                    // a pixel that is saturated or below the alpha threshold blends with weight 0, which is an exact no-op
+                    const float2 dy02 = make_float2(dy0, dy0), c22 = make_float2(c2, c2), lin2 = make_float2(lin, lin),
+                                 base2 = make_float2(base, base), os2 = make_float2(os, os);
+                    const float2 cr2 = make_float2(q1.z, q1.z), cg2 = make_float2(q1.w, q1.w), cb2 = make_float2(cb, cb),
+                                 nki2 = make_float2(-KI, -KI);
+#pragma unroll
+                    for (int p = 0; p < PPT / 2; p++) {
+                        const float2 dy = __fadd2_rn(dy02, make_float2(-(float)(2 * p), -(float)(2 * p + 1)));
+                        const float2 pw = __ffma2_rn(dy, __ffma2_rn(c22, dy, lin2), base2);
+                        const float2 t = __fmul2_rn(os2, make_float2(fast_ex2(pw.x), fast_ex2(pw.y)));
+                        const float a0 = __saturatef(t.x), a1 = __saturatef(t.y);      // min(alpha, 255/256) * 256/255
+                        const bool act0 = Ts[2 * p] > TS_MIN, act1 = Ts[2 * p + 1] > TS_MIN;
+                        if (act0) nf[2 * p] += 1.0f;
+                        if (act1) nf[2 * p + 1] += 1.0f;
+                        const float2 aw = make_float2((act0 && a0 >= A_MIN_S) ? a0 : 0.0f, (act1 && a1 >= A_MIN_S) ? a1 : 0.0f);
+                        const float2 w = __fmul2_rn(aw, make_float2(Ts[2 * p], Ts[2 * p + 1]));
+                        const float2 r2 = __ffma2_rn(cr2, w, make_float2(Cr[2 * p], Cr[2 * p + 1]));
+                        const float2 g2 = __ffma2_rn(cg2, w, make_float2(Cg[2 * p], Cg[2 * p + 1]));
+                        const float2 b2_ = __ffma2_rn(cb2, w, make_float2(Cb[2 * p], Cb[2 * p + 1]));
+                        const float2 tn = __ffma2_rn(nki2, w, make_float2(Ts[2 * p], Ts[2 * p + 1]));
+                        Cr[2 * p] = r2.x; Cr[2 * p + 1] = r2.y; Cg[2 * p] = g2.x; Cg[2 * p + 1] = g2.y;
+                        Cb[2 * p] = b2_.x; Cb[2 * p + 1] = b2_.y; Ts[2 * p] = tn.x; Ts[2 * p + 1] = tn.y;
+                    }
+                } else {
 #pragma unroll
                 for (int j = 0; j < PPT; j++) {
                     const float dy = dy0 - (float)j;
@@ -280,6 +307,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_forward_kernel(
                         if (ok) { fcount++; wsum += a * Ts[j]; }
                     }
                     blend_pixel(a, q1.z, q1.w, cb, Ts[j], Cr[j], Cg[j], Cb[j], nf[j], TS_MIN, A_MIN_S, -KI);
+                }
                 }
                 if (STAT) {
                     // per-(tile,splat) fragment statistics for densification (GR/raster.cu:288-301)
@@ -843,6 +871,18 @@ static bool use_deferred_reduce()
 }
 extern "C" int lgs_set_backward_reduce(int deferred) { g_defer = deferred ? 1 : 0; return LGS_OK; }
 
+// forward blend: 1 = packed pixel pairs, 0 = scalar predicated PTX body.  env LGS_FWD_PAIRS=0|1
+static int g_fwd_pairs = -1;
+static bool forward_pairs()
+{
+    if (g_fwd_pairs < 0) {
+        const char* e = getenv("LGS_FWD_PAIRS");
+        g_fwd_pairs = (e && e[0] == '1') ? 1 : 0;
+    }
+    return g_fwd_pairs == 1;
+}
+extern "C" int lgs_set_forward_pairs(int on) { g_fwd_pairs = on ? 1 : 0; return LGS_OK; }
+
 // backward kernel: 2 = packed-pair kernel (default), 1 = the scalar kernel (kept as A/B and for the TMA staging variant).
 // env LGS_BWD=v1|v2
 static int g_bwd = -1;
@@ -935,10 +975,13 @@ extern "C" int lgs_rasterize_forward_packed(const int* sorted_points, const int*
     const bool bulk = use_bulk();
 #define FWD(S, B) raster_forward_kernel<TH, TW, S, B><<<grid, block, 0, st>>>(sorted_points, start_index, recs, specific_tiles, n_specific, \
         img, transmittance, (unsigned short*)last_contributor, fragment_count, fragment_weight, tile_work, gx, ntile, cap, N, Hp, Wp, clamp_zero)
+#define FWDP() raster_forward_kernel<TH, TW, false, false, true><<<grid, block, 0, st>>>(sorted_points, start_index, recs, specific_tiles, \
+        n_specific, img, transmittance, (unsigned short*)last_contributor, fragment_count, fragment_weight, tile_work, gx, ntile, cap, N, Hp, Wp, clamp_zero)
     LGS_DISPATCH_TILE(tile_h, tile_w,
         if (enable_statistic) { if (bulk) FWD(true, true); else FWD(true, false); }
-        else { if (bulk) FWD(false, true); else FWD(false, false); })
+        else { if (bulk) FWD(false, true); else if (forward_pairs()) FWDP(); else FWD(false, false); })
 #undef FWD
+#undef FWDP
     LGS_CHECK_LAUNCH("raster_forward_kernel");
     return LGS_OK;
 }
