@@ -58,6 +58,7 @@ SIGNATURES = {
                                _P, _P, _P, _P, _P, _P, _P, _P],
     "lgs_set_staging": [_I],
     "lgs_set_sort_impl": [_I],
+    "lgs_set_radix_form": [_I],
     "lgs_set_warps_per_block": [_I],
     "lgs_set_backward_reduce": [_I],
     "lgs_set_backward_kernel": [_I],

@@ -220,6 +220,155 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const KeyT* __re
     }
 }
 
+// ---- single-read-per-pass form ("onesweep"): global digit histograms of ALL passes in one read of the keys, then one kernel
+// per pass that ranks a tile, obtains the number of same-digit keys in all EARLIER tiles by decoupled look-back (each tile
+// publishes its per-digit counts, then its inclusive prefix, in one 32-bit word per digit: 2 flag bits + 30-bit count) and
+// scatters.  Against the histogram / row-scan / scatter passes above this removes, per pass, one full read of the keys and two
+// latency-bound launches (the row scan alone is 6-10 us of a 13 us ... 60 us pass, profiles/ncu_all_kernels_r2_c2.txt).
+// The ranking and the shared-memory reorder are the ones of rs_scatter_kernel.  Tiles take their index from an atomic ticket, so a
+// tile's predecessors have always started: the look-back cannot dead-lock whatever order the hardware dispatches CTAs in.
+constexpr unsigned LB_AGG = 1u << 30, LB_INC = 2u << 30, LB_MASK = (1u << 30) - 1u;
+constexpr int RS_MAXPASS = 4;
+
+struct GhistArgs { int shift[RS_MAXPASS]; int nbins[RS_MAXPASS]; int passes; };
+
+template <typename KeyT, int IPT>
+__global__ void __launch_bounds__(RS_THREADS) rs_ghist_kernel(const KeyT* __restrict__ keys, int n, GhistArgs A, int* __restrict__ ghist,
+                                                              unsigned bias, const int* __restrict__ n_dev,
+                                                              const unsigned* __restrict__ bias_dev)
+{
+    constexpr int TILE = RS_THREADS * IPT;
+    __shared__ int h[RS_MAXPASS][RS_MAXBINS];
+    const int t = threadIdx.x;
+    if (n_dev != nullptr) n = min(n, max(*n_dev, 0));
+    if (bias_dev != nullptr) bias = *bias_dev;
+    const int base = blockIdx.x * TILE;
+    if (base >= n) return;
+    for (int p = 0; p < A.passes; p++) h[p][t] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < IPT; i++) {
+        const int idx = base + i * RS_THREADS + t;
+        if (idx < n) {
+            const unsigned k = (unsigned)keys[idx] - bias;
+            for (int p = 0; p < A.passes; p++) atomicAdd(&h[p][(k >> A.shift[p]) & (unsigned)(A.nbins[p] - 1)], 1);
+        }
+    }
+    __syncthreads();
+    for (int p = 0; p < A.passes; p++)
+        if (t < A.nbins[p] && h[p][t] != 0) atomicAdd(&ghist[p * RS_MAXBINS + t], h[p][t]);
+}
+
+template <typename KeyT, int IPT>
+__global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const KeyT* __restrict__ kin, const unsigned* __restrict__ vin,
+                                                                 KeyT* __restrict__ kout, unsigned* __restrict__ vout, int n, int shift,
+                                                                 int nbins, const int* __restrict__ ghist /* this pass: [RS_MAXBINS] */,
+                                                                 unsigned* __restrict__ status /* this pass: [tiles][nbins] */,
+                                                                 int* __restrict__ ticket, unsigned bias, const int* __restrict__ n_dev,
+                                                                 const unsigned* __restrict__ bias_dev)
+{
+    constexpr int TILE = RS_THREADS * IPT;
+    using BlockScan = cub::BlockScan<int, RS_THREADS>;
+    __shared__ int s_cnt[RS_WARPS][RS_MAXBINS];
+    __shared__ int s_gofs[RS_MAXBINS];
+    __shared__ KeyT s_k[TILE];
+    __shared__ unsigned s_v[TILE];
+    __shared__ int s_tile;
+    static_assert(TILE >= RS_WARPS * RS_MAXBINS, "the match slots alias the value staging buffer");
+    unsigned (*s_match)[RS_MAXBINS] = reinterpret_cast<unsigned (*)[RS_MAXBINS]>(s_v);
+    __shared__ typename BlockScan::TempStorage s_scan;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (n_dev != nullptr) n = min(n, max(*n_dev, 0));
+    if (bias_dev != nullptr) bias = *bias_dev;
+    if (t == 0) s_tile = atomicAdd(ticket, 1);
+#pragma unroll
+    for (int k = 0; k < RS_WARPS; k++) { s_cnt[k][t] = 0; s_match[k][t] = 0u; }
+    __syncthreads();
+    const int tile = s_tile;
+    const int base = tile * TILE;
+    if (base >= n) return;                                   // (uniform) tickets past the live range have nothing to do
+    const int nvalid = min(TILE, n - base);
+    const unsigned mask = (unsigned)nbins - 1u;
+    const unsigned lt = lanemask_lt();
+    KeyT key[IPT];
+    unsigned val[IPT];
+    unsigned short rank[IPT];
+#pragma unroll
+    for (int i = 0; i < IPT; i++) {
+        int loc = w * 32 * IPT + i * 32 + lane;
+        bool valid = loc < nvalid;
+        key[i] = valid ? kin[base + loc] : (KeyT)(bias - 1u);   // padding: digit of all ones, ranks after every real key of it
+        val[i] = valid ? vin[base + loc] : 0u;
+    }
+    // first output slot of each digit over the whole input (exclusive scan of the global histogram)
+    int gdig;
+    {
+        int tot_d = t < nbins ? ghist[t] : 0;
+        BlockScan(s_scan).ExclusiveSum(tot_d, gdig);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < IPT; i++) {
+        unsigned d = (((unsigned)key[i] - bias) >> shift) & mask;
+        atomicOr(&s_match[w][d], 1u << lane);
+        __syncwarp();
+        unsigned m = s_match[w][d];
+        int r = s_cnt[w][d] + __popc(m & lt);
+        rank[i] = (unsigned short)r;
+        __syncwarp();
+        if ((m >> lane) <= 1u) { s_cnt[w][d] = r + 1; s_match[w][d] = 0u; }
+        __syncwarp();
+    }
+    __syncthreads();
+    // digit t: exclusive scan of the per-warp counts -> this tile's count of digit t (padding keys excluded below)
+    int tot = 0;
+#pragma unroll
+    for (int k = 0; k < RS_WARPS; k++) { int c = s_cnt[k][t]; s_cnt[k][t] = tot; tot += c; }
+    // real keys of digit t in this tile: the padding keys all carry the all-ones digit of (bias - 1) - bias = 0xffff.. -> mask
+    int real = tot;
+    if (t == (int)mask) real -= (TILE - nvalid);
+    // decoupled look-back over the earlier tiles
+    if (t < nbins) {
+        volatile unsigned* st_ = status + (size_t)tile * nbins;
+        st_[t] = LB_AGG | (unsigned)real;
+        unsigned prefix = 0u;
+        for (int i = tile - 1; i >= 0;) {
+            const unsigned v = *((volatile unsigned*)(status + (size_t)i * nbins + t));
+            const unsigned flag = v & ~LB_MASK;
+            if (flag == 0u) continue;                        // predecessor has not published yet (it has started: tickets)
+            prefix += v & LB_MASK;
+            if (flag == LB_INC) break;
+            i--;
+        }
+        st_[t] = LB_INC | (prefix + (unsigned)real);
+        gdig += (int)prefix;
+    }
+    int dbase;
+    BlockScan(s_scan).ExclusiveSum(tot, dbase);
+#pragma unroll
+    for (int k = 0; k < RS_WARPS; k++) s_cnt[k][t] += dbase;
+    s_gofs[t] = gdig - dbase;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < IPT; i++) {
+        unsigned d = (((unsigned)key[i] - bias) >> shift) & mask;
+        int p = s_cnt[w][d] + rank[i];
+        s_k[p] = key[i];
+        s_v[p] = val[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < IPT; i++) {
+        int k = i * RS_THREADS + t;
+        if (k < nvalid) {
+            KeyT kk = s_k[k];
+            int dst = s_gofs[(((unsigned)kk - bias) >> shift) & mask] + k;
+            kout[dst] = kk;
+            vout[dst] = s_v[k];
+        }
+    }
+}
+
 struct RsPlan {
     int ipt, tile, nblocks, passes, dbits;
     size_t table_bytes, scan_bytes, total_bytes, off_scan, off_keys, off_vals;
@@ -238,14 +387,20 @@ RsPlan rs_plan(int n, int begin_bit, int end_bit)
     int bits = end_bit - begin_bit;
     p.passes = bits <= 0 ? 0 : (bits + 7) / 8;
     p.dbits = p.passes == 0 ? 0 : (bits + p.passes - 1) / p.passes;
-    p.table_bytes = align256((size_t)RS_MAXBINS * p.nblocks * sizeof(int));
-    p.scan_bytes = align256(RS_MAXBINS * sizeof(int));          // digit totals
+    // table: [digit][block] counts of one pass (pass form)  |  look-back status words of up to RS_MAXPASS passes (onesweep form)
+    p.table_bytes = align256((size_t)RS_MAXPASS * RS_MAXBINS * p.nblocks * sizeof(int));
+    p.scan_bytes = align256((RS_MAXPASS * RS_MAXBINS + 64) * sizeof(int));          // digit totals | global histograms + tickets
     p.off_scan = p.table_bytes;
     p.off_keys = p.off_scan + p.scan_bytes;
     p.off_vals = p.off_keys + align256((size_t)n * sizeof(KeyT));
     p.total_bytes = p.off_vals + align256((size_t)n * sizeof(unsigned));
     return p;
 }
+
+bool rs_use_onesweep();
+template <typename KeyT>
+int rs_sort_onesweep(const KeyT* keys_in, KeyT* keys_out, const unsigned* vals_in, unsigned* vals_out, int n, int begin_bit, int end_bit,
+                     unsigned bias, char* ws, cudaStream_t st, const int* n_dev, const unsigned* bias_dev);
 
 template <typename KeyT>
 int rs_sort(const KeyT* keys_in, KeyT* keys_out, const unsigned* vals_in, unsigned* vals_out, int n, int begin_bit, int end_bit,
@@ -258,6 +413,8 @@ int rs_sort(const KeyT* keys_in, KeyT* keys_out, const unsigned* vals_in, unsign
         LGS_CUDA(cudaMemcpyAsync(vals_out, vals_in, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
         return LGS_OK;
     }
+    if (rs_use_onesweep())
+        return rs_sort_onesweep<KeyT>(keys_in, keys_out, vals_in, vals_out, n, begin_bit, end_bit, bias, ws, st, n_dev, bias_dev);
     int* table = (int*)ws;
     int* totals = (int*)(ws + p.off_scan);
     KeyT* ktmp = (KeyT*)(ws + p.off_keys);
@@ -287,6 +444,62 @@ int rs_sort(const KeyT* keys_in, KeyT* keys_out, const unsigned* vals_in, unsign
         LGS_CHECK_LAUNCH("rs_scatter_kernel");
         ksrc = kdst; vsrc = vdst;
         bit += dbits;
+    }
+    return LGS_OK;
+}
+
+// 1 = onesweep form (default), 0 = histogram / row-scan / scatter passes.  env LGS_RS=passes|onesweep
+int g_rs_onesweep = -1;
+bool rs_use_onesweep()
+{
+    if (g_rs_onesweep < 0) {
+        const char* e = getenv("LGS_RS");
+        g_rs_onesweep = (e != nullptr && e[0] == 'p') ? 0 : 1;
+    }
+    return g_rs_onesweep == 1;
+}
+
+template <typename KeyT>
+int rs_sort_onesweep(const KeyT* keys_in, KeyT* keys_out, const unsigned* vals_in, unsigned* vals_out, int n, int begin_bit, int end_bit,
+                     unsigned bias, char* ws, cudaStream_t st, const int* n_dev, const unsigned* bias_dev)
+{
+    RsPlan p = rs_plan<KeyT>(n, begin_bit, end_bit);
+    unsigned* status = (unsigned*)ws;
+    int* ghist = (int*)(ws + p.off_scan);
+    int* tickets = ghist + RS_MAXPASS * RS_MAXBINS;
+    KeyT* ktmp = (KeyT*)(ws + p.off_keys);
+    unsigned* vtmp = (unsigned*)(ws + p.off_vals);
+    GhistArgs A;
+    A.passes = p.passes;
+    size_t status_words = 0;
+    int bit = begin_bit;
+    for (int pass = 0; pass < p.passes; pass++) {
+        int dbits = min(p.dbits, end_bit - bit);
+        A.shift[pass] = bit; A.nbins[pass] = 1 << dbits;
+        status_words += (size_t)p.nblocks * A.nbins[pass];
+        bit += dbits;
+    }
+    LGS_CUDA(cudaMemsetAsync(status, 0, status_words * sizeof(unsigned), st));
+    LGS_CUDA(cudaMemsetAsync(ghist, 0, (RS_MAXPASS * RS_MAXBINS + 64) * sizeof(int), st));
+    if (p.ipt == 16) rs_ghist_kernel<KeyT, 16><<<p.nblocks, RS_THREADS, 0, st>>>(keys_in, n, A, ghist, bias, n_dev, bias_dev);
+    else rs_ghist_kernel<KeyT, 8><<<p.nblocks, RS_THREADS, 0, st>>>(keys_in, n, A, ghist, bias, n_dev, bias_dev);
+    LGS_CHECK_LAUNCH("rs_ghist_kernel");
+    const KeyT* ksrc = keys_in;
+    const unsigned* vsrc = vals_in;
+    size_t soff = 0;
+    for (int pass = 0; pass < p.passes; pass++) {
+        bool to_out = ((p.passes - 1 - pass) & 1) == 0;
+        KeyT* kdst = to_out ? keys_out : ktmp;
+        unsigned* vdst = to_out ? vals_out : vtmp;
+        if (p.ipt == 16)
+            rs_onesweep_kernel<KeyT, 16><<<p.nblocks, RS_THREADS, 0, st>>>(ksrc, vsrc, kdst, vdst, n, A.shift[pass], A.nbins[pass],
+                                                                          ghist + pass * RS_MAXBINS, status + soff, tickets + pass, bias, n_dev, bias_dev);
+        else
+            rs_onesweep_kernel<KeyT, 8><<<p.nblocks, RS_THREADS, 0, st>>>(ksrc, vsrc, kdst, vdst, n, A.shift[pass], A.nbins[pass],
+                                                                         ghist + pass * RS_MAXBINS, status + soff, tickets + pass, bias, n_dev, bias_dev);
+        LGS_CHECK_LAUNCH("rs_onesweep_kernel");
+        soff += (size_t)p.nblocks * A.nbins[pass];
+        ksrc = kdst; vsrc = vdst;
     }
     return LGS_OK;
 }
@@ -337,6 +550,13 @@ extern "C" int lgs_set_sort_impl(int impl)
     LGS_REQUIRE(impl == 0 || impl == 1, "set_sort_impl: %d is not 0 (cub) or 1 (lgs)", impl);
     g_sort_impl = impl;
     g_sort_forced = true;
+    return LGS_OK;
+}
+
+// 1 = onesweep form of the own radix sort (default), 0 = histogram / row-scan / scatter passes; env LGS_RS=passes|onesweep
+extern "C" int lgs_set_radix_form(int onesweep)
+{
+    g_rs_onesweep = onesweep ? 1 : 0;
     return LGS_OK;
 }
 
