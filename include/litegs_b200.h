@@ -143,8 +143,8 @@ int lgs_tile_range_u16(const unsigned short* table_tile_id, int V, int table_len
  * cub::DeviceRadixSort::SortPairs (GR/binning.cu:204-221) for the tile sort.  keys_in/vals_in are not modified.
  * lgs_set_sort_impl: 1 = own histogram/scan/scatter passes (default), 0 = cub::DeviceRadixSort; env LGS_SORT=lgs|cub. */
 int lgs_set_sort_impl(int impl);
-/* form of the own radix sort: 1 = onesweep (global histograms in one read + decoupled look-back per pass; default),
- * 0 = histogram / row-scan / scatter passes; env LGS_RS=passes|onesweep */
+/* form of the own radix sort: 0 = histogram / row-scan / scatter passes (default, measured faster), 1 = onesweep (global
+ * histograms in one read + decoupled look-back per pass); env LGS_RS=passes|onesweep */
 int lgs_set_radix_form(int onesweep);
 int lgs_sort_pairs_u16_workspace_bytes(int n, size_t* bytes);
 int lgs_sort_pairs_u16(const unsigned short* keys_in, unsigned short* keys_out, const unsigned* vals_in, unsigned* vals_out,

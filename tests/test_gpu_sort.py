@@ -21,16 +21,16 @@ def _sort(keys, vals, begin, end, impl):
     _lib.call(f"lgs_sort_pairs{sfx}_workspace_bytes", max(n, 1), ctypes.byref(nb))
     ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
     ko, vo = torch.full_like(keys, -1), torch.full_like(vals, -1)
-    # impl: 1 = own sort, onesweep form (default) | 2 = own sort, histogram / row-scan / scatter passes | 0 = cub
+    # impl: 1 = own sort, histogram / row-scan / scatter passes (default) | 2 = own sort, onesweep form | 0 = cub
     _lib.call("lgs_set_sort_impl", 0 if impl == 0 else 1)
-    _lib.call("lgs_set_radix_form", 0 if impl == 2 else 1)
+    _lib.call("lgs_set_radix_form", 1 if impl == 2 else 0)
     try:
         _lib.call(f"lgs_sort_pairs{sfx}", ctypes.c_void_p(keys.data_ptr()), ctypes.c_void_p(ko.data_ptr()), ctypes.c_void_p(vals.data_ptr()),
                   ctypes.c_void_p(vo.data_ptr()), n, begin, end, ctypes.c_void_p(ws.data_ptr()), ctypes.c_size_t(nb.value),
                   ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     finally:
         _lib.call("lgs_set_sort_impl", 1)
-        _lib.call("lgs_set_radix_form", 1)
+        _lib.call("lgs_set_radix_form", 0)
     torch.cuda.synchronize()
     return ko, vo
 
@@ -52,7 +52,7 @@ CASES = [  # dtype, n, begin, end, key generator
 ]
 
 
-@pytest.mark.parametrize("impl", [1, 2, 0], ids=["lgs", "lgs_passes", "cub"])
+@pytest.mark.parametrize("impl", [1, 2, 0], ids=["lgs", "lgs_onesweep", "cub"])
 @pytest.mark.parametrize("dtype,n,begin,end,kind", CASES)
 def test_sort_pairs_matches_stable_sort(cuda, impl, dtype, n, begin, end, kind):
     g = torch.Generator(device="cpu").manual_seed(n + 31 * end)
@@ -80,7 +80,7 @@ def test_sort_pairs_matches_stable_sort(cuda, impl, dtype, n, begin, end, kind):
     assert torch.equal(ko, ek)
 
 
-@pytest.mark.parametrize("impl", [1, 2, 0], ids=["lgs", "lgs_passes", "cub"])
+@pytest.mark.parametrize("impl", [1, 2, 0], ids=["lgs", "lgs_onesweep", "cub"])
 def test_rebased_depth_sort_orders_keys_inside_the_range(cuda, impl):
     """lgs_sort_pairs_u32_rebased: keys inside [bias, bias + 2^bits) come out in full-key stable order; the keys outside
     (culled splats, all ones) may land anywhere but must all still be present."""
@@ -100,14 +100,14 @@ def test_rebased_depth_sort_orders_keys_inside_the_range(cuda, impl):
     ws = torch.empty(nb.value, dtype=torch.uint8, device=cuda)
     ko, vo = torch.empty_like(keys), torch.empty_like(vals)
     _lib.call("lgs_set_sort_impl", 0 if impl == 0 else 1)
-    _lib.call("lgs_set_radix_form", 0 if impl == 2 else 1)
+    _lib.call("lgs_set_radix_form", 1 if impl == 2 else 0)
     try:
         _lib.call("lgs_sort_pairs_u32_rebased", ctypes.c_void_p(keys.data_ptr()), ctypes.c_void_p(ko.data_ptr()),
                   ctypes.c_void_p(vals.data_ptr()), ctypes.c_void_p(vo.data_ptr()), n, kmin, bits, ctypes.c_void_p(ws.data_ptr()),
                   ctypes.c_size_t(nb.value), None)
     finally:
         _lib.call("lgs_set_sort_impl", 1)
-        _lib.call("lgs_set_radix_form", 1)
+        _lib.call("lgs_set_radix_form", 0)
     torch.cuda.synchronize()
     vo_c, ko_c = vo.cpu().long(), ko.cpu()
     assert torch.equal(torch.sort(vo_c).values, torch.arange(n))      # a permutation
