@@ -768,6 +768,8 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         pr = [[float(x) for x in gthr.tolist()] for gthr in gathered]
         comm = {"allreduce": args.allreduce if args.level == "B" else "sync", "bytes_per_step": int(accs[0].flat.numel() * 4),
+                "allreduce_impl": ("own NVLS kernel over the buffer's NVSwitch multicast address (multimem.ld_reduce / multimem.st, csrc/nvls.cu)"
+                                   if accs[0]._nvls is not None else "ncclAllReduce"),
                 "allreduce_ms_per_step_rank0": comm_ms,
                 "allreduce_ms_per_step_by_rank": [r_[1] / args.steps for r_ in pr],
                 "step_ms_by_rank": [r_[0] / args.steps for r_ in pr],

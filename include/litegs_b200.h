@@ -307,6 +307,13 @@ int lgs_adam_step_dense(float* const* params, const int* rows_per_param, const f
 int lgs_sparse_chunk_op(void* A, const void* B, const int64_t* visible_chunk_ids, const int* visible_count, int dtype,
                         int op, int ele_num, int chunks, int alloc_chunks, int chunk_size, void* stream);
 
+/* ---- multi-GPU exchange (new: the reference is single-GPU) ---------------------------------------------------------
+ * The per-step all-reduce of the dense gradient buffer as one kernel over the buffer's NVSwitch MULTICAST address
+ * (multimem.ld_reduce / multimem.st, reduction inside the switch).  multicast_ptr: multicast mapping of a symmetric allocation of
+ * n_floats floats (multiple of 4) present on every rank; the caller puts a cross-GPU barrier on the stream before and after.
+ * ctas = 0 selects the default grid. */
+int lgs_nvls_allreduce_f32(float* multicast_ptr, size_t n_floats, int rank, int world, int ctas, void* stream);
+
 /* ---- chunk maintenance between epochs ----------------------------------------------------------------- */
 
 /* Morton codes of _gen_morton_code (litegs/scene/point.py:38-81): xyz f32[3,N], lo3/hi3 DEVICE f32[3] (per-axis min / max),

@@ -73,6 +73,7 @@ SIGNATURES = {
     "lgs_adam_update_primitive": [_P, _P, _P, _P, _P, _I, _I, _D, _D, _D, _D, _P],
     "lgs_sparse_chunk_op": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "lgs_mark_visible_chunks": [_P, _P, _I, _P, _P],
+    "lgs_nvls_allreduce_f32": [_P, _Z, _I, _I, _I, _P],
     "lgs_morton_codes": [_P, _P, _P, _I, _I, _P, _P],
     "lgs_permute_rows": [_P, _P, _I, _I, _P, _P],
     "lgs_cluster_aabb": [_P, _P, _P, _I, _I, _P, _P, _P],

@@ -9,6 +9,7 @@ buffer (views see different visible-chunk sets, so the sum over views is dense) 
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -48,14 +49,40 @@ class GradAccumulator:
         # one allocation = one all-reduce: [rows*C*S gradient | C chunk marks].  The marks say which chunks were visible
         # in at least one view of the step (on any rank after the reduce); the fused optimizer step updates only those,
         # the reference's sparse-Adam semantics (optimizer.py:14-44).
-        self.flat = torch.zeros(n_rows * C * S + C, dtype=torch.float32, device=dev)
+        n_flat = n_rows * C * S + C
+        self._nvls = None                   # symmetric-memory handle when the buffer is mapped for NVSwitch multicast
+        self.flat_all = self._allocate(n_flat, dev)
+        self.flat = self.flat_all[:n_flat]
         self.buf = self.flat[: n_rows * C * S].view(n_rows, C, S)
         self.touched = self.flat[n_rows * C * S:]
         self._work = None
         self._comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
 
+    def _allocate(self, n_flat: int, dev) -> torch.Tensor:
+        """The flat buffer.  On a multi-GPU NCCL job it is symmetric memory mapped for NVSwitch multicast when the platform offers
+        it (torch.distributed._symmetric_memory; LGS_NVLS=0 opts out), so that all_reduce() can run the library's own NVLS kernel
+        (csrc/nvls.cu) instead of ncclAllReduce; otherwise an ordinary allocation reduced by the backend's all-reduce."""
+        import torch.distributed as dist
+        n_pad = (n_flat + 3) // 4 * 4
+        if (dev.type == "cuda" and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+                and dist.get_backend() == "nccl" and os.environ.get("LGS_NVLS", "1") != "0"):
+            try:
+                import torch.distributed._symmetric_memory as symm
+                t = symm.empty(n_pad, dtype=torch.float32, device=dev)
+                hdl = symm.rendezvous(t, dist.group.WORLD)
+                if int(hdl.multicast_ptr) == 0:
+                    raise RuntimeError("no multicast support")
+                t.zero_()
+                self._nvls = hdl
+                return t
+            except Exception as e:      # noqa: BLE001 -- any failure of the optional fast path falls back to NCCL, loudly once
+                if os.environ.get("RANK", "0") == "0":
+                    print(f"[litegs_b200.dist] NVLS all-reduce unavailable ({type(e).__name__}: {str(e)[:120]}); using the NCCL all-reduce")
+                self._nvls = None
+        return torch.zeros(n_pad, dtype=torch.float32, device=dev)
+
     def zero_(self):
-        self.flat.zero_()
+        self.flat_all.zero_()
 
     def mark(self, chunk_ids: torch.Tensor, visible_count: torch.Tensor):
         """touched[chunk_ids[j]] = 1 for j < *visible_count (device count: no sync)."""
@@ -95,12 +122,32 @@ class GradAccumulator:
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return
+        if self._nvls is not None:
+            if self._comm_stream is not None and async_op:
+                self._comm_stream.wait_stream(torch.cuda.current_stream(self.buf.device))
+                with torch.cuda.stream(self._comm_stream):
+                    self._nvls_all_reduce()
+            else:
+                self._nvls_all_reduce()
+            return
         if self._comm_stream is not None and async_op:
             self._comm_stream.wait_stream(torch.cuda.current_stream(self.buf.device))
             with torch.cuda.stream(self._comm_stream):
                 self._work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=True)
         else:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+
+    def _nvls_all_reduce(self):
+        """barrier (every replica complete) -> one multimem kernel: each rank reduces its slice inside the switch and broadcasts it
+        -> barrier (every slice delivered), all on the current stream."""
+        from . import _lib
+        hdl = self._nvls
+        dev = self.buf.device
+        st = torch.cuda.current_stream(dev).cuda_stream
+        hdl.barrier(channel=0, timeout_ms=60000)
+        _lib.call("lgs_nvls_allreduce_f32", ctypes.c_void_p(int(hdl.multicast_ptr)), ctypes.c_size_t(self.flat_all.numel()), int(hdl.rank),
+                  int(hdl.world_size), int(os.environ.get("LGS_NVLS_CTAS", "0")), st)
+        hdl.barrier(channel=0, timeout_ms=60000)
 
     def wait(self):
         if self._work is not None:

@@ -43,7 +43,8 @@ def main():
     torch.cuda.synchronize()
     loss_sum = torch.stack(losses).sum().reshape(1).double()
     dist.all_reduce(loss_sum)
-    out = {"world": world, "views": n_views}
+    out = {"world": world, "views": n_views,
+           "allreduce_impl": "own NVLS multimem kernel (csrc/nvls.cu)" if acc._nvls is not None else "ncclAllReduce"}
     if rank == 0:
         ref = lgs_dist.GradAccumulator(P)
         ref_losses = render_into(ref, list(range(n_views)))
