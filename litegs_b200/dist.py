@@ -40,7 +40,10 @@ class GradAccumulator:
     """Dense gradient buffer [rows, C, S] (fp32): sum of the compacted per-view gradients of this rank, then
     all-reduced (sum) over ranks.  59 rows at sh_degree 3 => 236 B per Gaussian."""
 
-    def __init__(self, params: Dict[str, torch.Tensor]):
+    def __init__(self, params: Dict[str, torch.Tensor], symmetric: Optional[bool] = None):
+        """symmetric: map the buffer for the own NVLS all-reduce kernel (a COLLECTIVE allocation: every rank must construct the
+        accumulator).  None = env LGS_NVLS=1 (default off: ncclAllReduce); False for a rank-local buffer."""
+        self._want_symmetric = (os.environ.get("LGS_NVLS", "0") == "1") if symmetric is None else bool(symmetric)
         self.shapes = {k: tuple(params[k].shape) for k in PARAM_ORDER}
         self.rows = param_rows(self.shapes)
         C, S = self.shapes["xyz"][-2:]
@@ -60,12 +63,12 @@ class GradAccumulator:
 
     def _allocate(self, n_flat: int, dev) -> torch.Tensor:
         """The flat buffer.  On a multi-GPU NCCL job it is symmetric memory mapped for NVSwitch multicast when the platform offers
-        it (torch.distributed._symmetric_memory; LGS_NVLS=0 opts out), so that all_reduce() can run the library's own NVLS kernel
+        it and the caller asks for it (torch.distributed._symmetric_memory; LGS_NVLS=1 or symmetric=True), so that all_reduce() can run the library's own NVLS kernel
         (csrc/nvls.cu) instead of ncclAllReduce; otherwise an ordinary allocation reduced by the backend's all-reduce."""
         import torch.distributed as dist
         n_pad = (n_flat + 3) // 4 * 4
         if (dev.type == "cuda" and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-                and dist.get_backend() == "nccl" and os.environ.get("LGS_NVLS", "1") != "0"):
+                and dist.get_backend() == "nccl" and self._want_symmetric):
             try:
                 import torch.distributed._symmetric_memory as symm
                 t = symm.empty(n_pad, dtype=torch.float32, device=dev)

@@ -46,7 +46,7 @@ def main():
     out = {"world": world, "views": n_views,
            "allreduce_impl": "own NVLS multimem kernel (csrc/nvls.cu)" if acc._nvls is not None else "ncclAllReduce"}
     if rank == 0:
-        ref = lgs_dist.GradAccumulator(P)
+        ref = lgs_dist.GradAccumulator(P, symmetric=False)      # rank-local: a symmetric allocation would be a collective
         ref_losses = render_into(ref, list(range(n_views)))
         torch.cuda.synchronize()
         a, b = acc.buf.double(), ref.buf.double()

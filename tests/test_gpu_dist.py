@@ -14,13 +14,13 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("nvls", ["1", "0"], ids=["own_nvls_kernel_if_available", "nccl"])
+@pytest.mark.parametrize("nvls", ["0", "1"], ids=["nccl", "own_nvls_kernel_if_available"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_nccl_all_reduce_equals_single_rank_sum(cuda, world, nvls):
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs, this box has {torch.cuda.device_count()}")
-    port = 29500 + world + (20 if nvls == "0" else 0)
+    port = 29500 + world + (20 if nvls == "1" else 0)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "dist_nccl_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env={**os.environ, "LGS_NVLS": nvls})
