@@ -177,9 +177,9 @@ def render_view(cluster_origin, cluster_extend, frustumplane, view_matrix, proj_
                 xyz, scale, rot, sh_0, sh_rest, opacity, actived_sh_degree: int, output_shape, pp, accumulate_into=None):
     """render_preprocess + render of one view on the fused pipeline.
 
-    Same inputs as the two reference calls (raw clustered parameters, chunk AABBs, camera); returns
-    (img [1,3,H,W] clamped to [0,1], transmittance or None, depth=None, normal=None, visible_chunkid,
-    last_contributor).  Gradients reach the six parameter tensors as CompactedTensor (pp.sparse_grad) or dense
+    Same inputs as the two reference calls (raw clustered parameters, chunk AABBs, camera); returns the five values of the
+    reference's render() with the contributor counts in the last slot: (img [1,3,H,W] clamped to [0,1], transmittance or
+    None, depth=None, normal=None, last_contributor [1,1,Hp,Wp]).  Gradients reach the six parameter tensors as CompactedTensor (pp.sparse_grad) or dense
     tensors -- or, with ``accumulate_into`` (dict of dense gradient tensors, e.g. ``GradAccumulator.grads()``), are
     ADDED into those buffers by the backward kernel itself and ``param.grad`` stays untouched (multi-view batches,
     data-parallel training)."""
