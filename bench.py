@@ -633,15 +633,19 @@ def run_ours(args, rank, world, local_rank):
             gt_consumed[j] = ev
             if img is None:
                 return d_img
-            loss = torch.dot(img.reshape(-1), d_img.reshape(-1))
-            loss_hosts[step_no["k"] % 2][j:j + 1].copy_(loss.reshape(1), non_blocking=True)
+            with torch.no_grad():          # img may be an autograd leaf (render_views' loss_fn form): the gradient is returned explicitly,
+                loss = torch.dot(img.reshape(-1), d_img.reshape(-1))    # and a graph hanging off the pinned result buffer would keep every d_img alive
+            loss_hosts[step_no["k"] % 2][j:j + 1].copy_(loss.detach().reshape(1), non_blocking=True)
             return loss, d_img
 
         def read_losses(k):         # D2H results of step k: wait for its event, then read the pinned buffer
             loss_ev[k % 2].synchronize()
-            losses.append(float(loss_hosts[k % 2].sum()))
+            losses.append(float(loss_hosts[k % 2].detach().sum()))
+
+        trace = [] if os.environ.get("LGS_E2E_TRACE") == "1" else None     # diagnostic: per-step host enqueue / wait times + device step ends
 
         def e2e_step():
+            t_a = time.perf_counter()
             a = accs[step_no["k"] % len(accs)]
             a.wait()
             a.zero_()
@@ -649,12 +653,16 @@ def run_ours(args, rank, world, local_rank):
             reduce_step(a, False)                                      # same schedule as the resident-input loop
             k = step_no["k"]
             if args.level == "A":
-                loss_hosts[k % 2].copy_(torch.stack(out).reshape(-1), non_blocking=True)
+                loss_hosts[k % 2].copy_(torch.stack(out).detach().reshape(-1), non_blocking=True)
             loss_ev[k % 2].record(torch.cuda.current_stream(dev))     # render_views has joined the view streams into this one
             step_no["k"] += 1
+            t_b = time.perf_counter()
             if pending["k"] is not None:
                 read_losses(pending["k"])                             # previous step's result, now that this one is enqueued
             pending["k"] = k
+            if trace is not None:
+                ev = torch.cuda.Event(enable_timing=True); ev.record(torch.cuda.current_stream(dev))
+                trace.append((t_b - t_a, time.perf_counter() - t_b, ev))
 
         def e2e_drain():
             if pending["k"] is not None:
@@ -682,6 +690,16 @@ def run_ours(args, rank, world, local_rank):
             if world > 1:
                 dist.all_reduce(t2, op=dist.ReduceOp.MAX)
             reps.append(vpr * world * n_e2e / (float(t2.item()) / 1000.0))
+        if trace:
+            torch.cuda.synchronize(dev)
+            enq = sorted(((t[0] * 1e3, i) for i, t in enumerate(trace)), reverse=True)[:8]
+            waits = sorted(((t[1] * 1e3, i) for i, t in enumerate(trace)), reverse=True)[:8]
+            gaps = sorted(((trace[i][2].elapsed_time(trace[i + 1][2]), i + 1) for i in range(len(trace) - 1)), reverse=True)[:8]
+            med = lambda xs: sorted(xs)[len(xs) // 2]
+            print(f"[e2e trace rank {rank}] steps {len(trace)}  median enqueue {med([t[0] for t in trace]) * 1e3:.2f} ms  median wait "
+                  f"{med([t[1] for t in trace]) * 1e3:.2f} ms\n  longest host enqueue (ms, step): {[(round(a_, 1), i) for a_, i in enq]}\n"
+                  f"  longest host wait for step k-1 (ms, step): {[(round(a_, 1), i) for a_, i in waits]}\n"
+                  f"  longest device step-to-step gaps (ms, step): {[(round(a_, 1), i) for a_, i in gaps]}", file=sys.stderr)
         e2e = {"value": sorted(reps)[2], "unit": UNIT,
                "h2d_bytes_per_step": int(h2d * vpr), "d2h_bytes_per_step": int(4 * vpr), "steps": n_e2e, "repetitions": reps,
                "note": "median of five timed regions of K steps; per view: pinned camera H2D on the view's stream, uint8 target H2D on a copy "
