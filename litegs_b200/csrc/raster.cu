@@ -150,16 +150,31 @@ struct Stager {
         }
     }
     // wait until buffer `which` has landed; `more_in_flight` tells whether a younger group exists.
+    // PRE: lane l then rewrites ITS record of the shared-memory copy into the form the pixel loops consume -- the conic pre-multiplied
+    // for ex2 (A,B,C -> -0.5 log2e A, -log2e B, -0.5 log2e C) and o 256/255 in the depth slot -- so that these four multiplies are
+    // done once per record instead of once per record by each of the 32 lanes (same fp32 products, bit-identical results).
+    template <bool PRE = false>
     __device__ __forceinline__ void wait(int which, bool more_in_flight)
     {
         if (BULK) {
             mbar_wait(&bar[which], (phase_bits >> which) & 1u);
             phase_bits ^= (1u << which);
             pending &= ~(1u << which);
+            if (PRE) { prescale(which); __syncwarp(); }
         } else {
             if (more_in_flight) cp_async_wait<1>(); else cp_async_wait<0>();
+            if (PRE) prescale(which);            // the lane's own copy has landed (it waited on its own group)
             __syncwarp();
         }
+    }
+    __device__ __forceinline__ void prescale(int which)
+    {
+        SplatRec* r = buf + which * 32 + lane;
+        const float2 ab = *reinterpret_cast<const float2*>(&r->A);
+        const float2 co = *reinterpret_cast<const float2*>(&r->C);
+        *reinterpret_cast<float2*>(&r->A) = make_float2((-0.5f * LOG2E) * ab.x, (-LOG2E) * ab.y);
+        r->C = (-0.5f * LOG2E) * co.x;
+        r->depth = co.y * (256.0f / 255.0f);
     }
     // nothing may still be writing this CTA's shared memory when the warp leaves
     __device__ __forceinline__ void drain()
@@ -247,7 +262,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_forward_kernel(
                 int nn = (c + 2) * 32 + lane;
                 id_next = (nn < count) ? ids[nn] : -1;
             }
-            st.wait(c & 1, more);
+            st.template wait<true>(c & 1, more);
             const SplatRec* chunk = &s_rec[warp][c & 1][0];
             const int nk = min(32, count - c * 32);
             int my_id = 0;
@@ -263,13 +278,14 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_forward_kernel(
                     for (int j = 1; j < PPT; j++) tmax = fmaxf(tmax, Ts[j]);
                     if (!__any_sync(FULL_MASK, tmax > TS_MIN)) { done = true; break; }
                 }
-                const float4 q0 = *reinterpret_cast<const float4*>(&chunk[k].px);   // px py A B
-                const float4 q1 = *reinterpret_cast<const float4*>(&chunk[k].C);    // C o r g
-                const float cb = chunk[k].b;
+                const float4 q0 = *reinterpret_cast<const float4*>(&chunk[k].px);   // px py a2 b2   (pre-scaled by Stager::wait<true>)
+                const float4 q1 = *reinterpret_cast<const float4*>(&chunk[k].C);    // c2 o r g
+                const float2 q2 = *reinterpret_cast<const float2*>(&chunk[k].b);    // b, o 256/255
+                const float cb = q2.x;
                 const float dx = q0.x - fx, dy0 = q0.y - fy0;
-                const float a2 = (-0.5f * LOG2E) * q0.z, b2 = (-LOG2E) * q0.w, c2 = (-0.5f * LOG2E) * q1.x;
+                const float a2 = q0.z, b2 = q0.w, c2 = q1.x;
                 const float base = a2 * dx * dx, lin = b2 * dx;
-                const float os = q1.y * KS;
+                const float os = q2.y;
                 int fcount = 0; float wsum = 0.f;
                 if (PAIRS && !STAT) {
                     // packed-pair form (fma/mul/add.rn.f32x2): the two pixels of a pair share every instruction of the chain;
@@ -592,6 +608,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_v2_kerne
     __shared__ __align__(128) SplatRec s_rec[WARPS_PER_BLOCK][2][32];
     __shared__ __align__(8) uint64_t s_bar[WARPS_PER_BLOCK][2];
     __shared__ __align__(16) float s_acc[WARPS_PER_BLOCK][LGS_RG * NV][LGS_ROWF];
+    __shared__ int s_pid[WARPS_PER_BLOCK][4];               // ids of the splats parked in s_acc
     const int lane = threadIdx.x, warp = threadIdx.y, b = blockIdx.y;
     const int slot = blockIdx.x * blockDim.y + warp;
     int tile_id;
@@ -634,7 +651,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_v2_kerne
     kmax = __reduce_max_sync(FULL_MASK, kmax);
     if (kmax <= 0) return;
 
-    int pend = 0, pid0 = 0, pid1 = 0, pid2 = 0;        // splats parked in s_acc and their ids (warp-uniform)
+    int pend = 0;                                      // splats parked in s_acc (warp-uniform); their ids are in s_pid
     auto flush = [&]() {
         __syncwarp();
         if (lane < pend * NV) {
@@ -653,7 +670,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_v2_kerne
             p0 = __fadd2_rn(p0, p4);
             const float sum = p0.x + p0.y;
             const int sp = lane / NV, v = lane - sp * NV;
-            const int pid = sp == 0 ? pid0 : (sp == 1 ? pid1 : pid2);
+            const int pid = s_pid[warp][sp];
             if (DET) {
                 unsigned long long* gq = reinterpret_cast<unsigned long long*>(grad);
                 atomicAdd(&gq[(size_t)pid * LGS_GRAD_FLOATS + v], (unsigned long long)__double2ll_rn((double)sum * LGS_DET_SCALE));
@@ -680,20 +697,21 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_v2_kerne
             id_cur = id_next;
             id_next = (c >= 2) ? ids[(c - 2) * 32 + lane] : -1;
         }
-        st.wait(v & 1, more);
+        st.template wait<true>(v & 1, more);
         const SplatRec* chunk = &s_rec[warp][v & 1][0];
         const int nk = min(32, kmax - c * 32);
         for (int kk = nk - 1; kk >= 0; kk--) {
             const int k = c * 32 + kk;
-            const float4 q0 = *reinterpret_cast<const float4*>(&chunk[kk].px);   // px py A B
-            const float4 q1 = *reinterpret_cast<const float4*>(&chunk[kk].C);    // C o r g
-            const float cb = chunk[kk].b;
+            const float4 q0 = *reinterpret_cast<const float4*>(&chunk[kk].px);   // px py a2 b2   (pre-scaled by Stager::wait<true>)
+            const float4 q1 = *reinterpret_cast<const float4*>(&chunk[kk].C);    // c2 o r g
+            const float2 q2 = *reinterpret_cast<const float2*>(&chunk[kk].b);    // b, o 256/255
+            const float cb = q2.x;
             const float dx = q0.x - fx, dy0 = q0.y - fy0;
-            const float a2 = (-0.5f * LOG2E) * q0.z, b2 = (-LOG2E) * q0.w, c2 = (-0.5f * LOG2E) * q1.x;
+            const float a2 = q0.z, b2 = q0.w, c2 = q1.x;
             const float base = a2 * dx * dx, lin = b2 * dx;
-            const float2 os2 = bc2(q1.y * KS), o2 = bc2(q1.y), c22 = bc2(c2), lin2 = bc2(lin), base2 = bc2(base);
+            const float2 os2 = bc2(q2.y), o2 = bc2(q1.y), c22 = bc2(c2), lin2 = bc2(lin), base2 = bc2(base);
             const float2 cr2 = bc2(q1.z), cg2 = bc2(q1.w), cb2 = bc2(cb), dy02 = bc2(dy0);
-            float2 s0 = bc2(0.f), s1 = bc2(0.f), s2 = bc2(0.f), dr = bc2(0.f), dg = bc2(0.f), db = bc2(0.f);
+            float2 s0, s1, s2, dr, dg, db;              // per-(tile, splat) sums: the first pixel pair initialises them
             float esq = 0.f, runx = 0.f, runy = 0.f;
             bool any = false;
 #pragma unroll
@@ -713,9 +731,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_v2_kerne
                 const float2 a = make_float2(fminf(at.x, ALPHA_MAX), fminf(at.y, ALPHA_MAX));
                 const float2 om = __ffma2_rn(a, bc2(-1.0f), bc2(1.0f));                  // 1 - a
                 const float2 rc = make_float2(fast_rcp(om.x), fast_rcp(om.y));
-                float2 Tn = __fmul2_rn(T[p], rc);                                        // transmittance in front of this splat
-                Tn.x = fminf(1.0f, Tn.x); Tn.y = fminf(1.0f, Tn.y);
-                T[p] = Tn;
+                const float2 Tn = __fmul2_rn(T[p], rc);                                  // transmittance in front of this splat
+                T[p] = Tn;                                                               // (rc = 1 exactly where G was zeroed)
                 const float2 w = __fmul2_rn(a, Tn);
                 const float2 cgd = __ffma2_rn(cr2, g0[p], __ffma2_rn(cg2, g1[p], __fmul2_rn(cb2, g2[p])));
                 const float2 diff = __ffma2_rn(S[p], bc2(-1.0f), cgd);                   // (c - R) . g
@@ -723,11 +740,16 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_v2_kerne
                 if (TRANS) da = __ffma2_rn(ngt[p], rc, da);
                 S[p] = __ffma2_rn(a, diff, S[p]);
                 const float2 dpw = __fmul2_rn(at, da);      // passes through the 255/256 clamp (GR/raster.cu:776-778)
-                dr = __ffma2_rn(w, g0[p], dr); dg = __ffma2_rn(w, g1[p], dg); db = __ffma2_rn(w, g2[p], db);
-                s0 = __fadd2_rn(s0, dpw);
                 const float2 td = __fmul2_rn(dpw, dy);
-                s1 = __fadd2_rn(s1, td);
-                s2 = __ffma2_rn(td, dy, s2);
+                if (p == 0) {
+                    dr = __fmul2_rn(w, g0[p]); dg = __fmul2_rn(w, g1[p]); db = __fmul2_rn(w, g2[p]);
+                    s0 = dpw; s1 = td; s2 = __fmul2_rn(td, dy);
+                } else {
+                    dr = __ffma2_rn(w, g0[p], dr); dg = __ffma2_rn(w, g1[p], dg); db = __ffma2_rn(w, g2[p], db);
+                    s0 = __fadd2_rn(s0, dpw);
+                    s1 = __fadd2_rn(s1, td);
+                    s2 = __ffma2_rn(td, dy, s2);
+                }
                 if (STAT) {
                     const float2 go = __fmul2_rn(G, da);
                     if (err_mode == 1) {
@@ -744,7 +766,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_v2_kerne
                 // raw moments (LGS_GRAD_* slots, common.cuh): the conic factors are applied once per splat by the consumer
                 const float m0 = s0.x + s0.y, m1 = s1.x + s1.y, m2 = s2.x + s2.y;
                 const float u0 = dx * m0;
-                const int pid = __shfl_sync(FULL_MASK, id_this, kk);
+                if (lane == kk) s_pid[warp][pend] = id_this;
                 float* row = &s_acc[warp][pend * NV][lane];
                 row[0 * LGS_ROWF] = u0;                    // sum dx s0
                 row[1 * LGS_ROWF] = m1;                    // sum s1
@@ -756,7 +778,6 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) raster_backward_v2_kerne
                 row[7 * LGS_ROWF] = db.x + db.y;
                 row[8 * LGS_ROWF] = m0;                    // sum s0
                 if (STAT) row[9 * LGS_ROWF] = esq;
-                if (pend == 0) pid0 = pid; else if (pend == 1) pid1 = pid; else pid2 = pid;
                 pend++;
                 if (pend == LGS_RG) flush();
             }

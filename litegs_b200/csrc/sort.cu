@@ -129,14 +129,20 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scan_rows_kernel(int* __restric
 }
 
 // table[d * nblocks + b] = keys with digit d in blocks before b;  totals[d] = keys with digit d
-template <typename KeyT, int IPT>
-__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const KeyT* __restrict__ kin, const unsigned* __restrict__ vin,
+// NS = keys of a lane ranked per round of the warp-level ranking (1, 2 or 4): each of the NS items ORs its lane bit into its OWN set
+// of match slots, one __syncwarp later item j reads the count of its digit, the group sizes of that digit in the items before it
+// and its own group's mask -- all independent loads -- and the highest lane of every group publishes the group size with one
+// ATOMS.ADD.  The three warp barriers and the dependent ATOMS -> LDS -> STS chain of a round are paid once per NS keys instead of
+// once per key (the kernel was latency bound: 0.57 eligible warps per scheduler, profiles/ncu_all_kernels_r2_c2.txt launch 16).
+template <typename KeyT, int IPT, int NS>
+__global__ void __launch_bounds__(RS_THREADS, IPT == 16 ? 3 : 4) rs_scatter_kernel(const KeyT* __restrict__ kin, const unsigned* __restrict__ vin,
                                                                 KeyT* __restrict__ kout, unsigned* __restrict__ vout, int n, int shift,
                                                                 int nbins, int nblocks, const int* __restrict__ table,
                                                                 const int* __restrict__ totals, unsigned bias,
                                                                 const int* __restrict__ n_dev, const unsigned* __restrict__ bias_dev)
 {
     constexpr int TILE = RS_THREADS * IPT;
+    static_assert(IPT % NS == 0, "the ranking rounds must tile the items of a lane");
     if (n_dev != nullptr) n = min(n, max(*n_dev, 0));
     if (bias_dev != nullptr) bias = *bias_dev;
     if ((int)blockIdx.x * TILE >= n) return;
@@ -145,8 +151,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const KeyT* __re
     __shared__ int s_gofs[RS_MAXBINS];
     __shared__ KeyT s_k[TILE];
     __shared__ unsigned s_v[TILE];
-    static_assert(TILE >= RS_WARPS * RS_MAXBINS, "the match slots alias the value staging buffer");
-    unsigned (*s_match)[RS_MAXBINS] = reinterpret_cast<unsigned (*)[RS_MAXBINS]>(s_v);   // live only while ranking
+    unsigned* s_match = s_v;                 // [NS][RS_WARPS][nbins] match slots, live only while ranking (host: NS*RS_WARPS*nbins <= TILE)
     __shared__ typename BlockScan::TempStorage s_scan;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const int base = blockIdx.x * TILE;
@@ -154,7 +159,8 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const KeyT* __re
     const unsigned mask = (unsigned)nbins - 1u;
     const unsigned lt = lanemask_lt();
 #pragma unroll
-    for (int k = 0; k < RS_WARPS; k++) { s_cnt[k][t] = 0; s_match[k][t] = 0u; }
+    for (int k = 0; k < RS_WARPS; k++) s_cnt[k][t] = 0;
+    for (int k = t; k < NS * RS_WARPS * nbins; k += RS_THREADS) s_match[k] = 0u;
     // warp-striped tile: item i of lane l of warp w is element w*32*IPT + i*32 + l, so (w, i, l) order is index order
     KeyT key[IPT];
     unsigned val[IPT];
@@ -174,19 +180,38 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const KeyT* __re
         if (t < nbins) gdig += table[(size_t)t * nblocks + blockIdx.x];
     }
     __syncthreads();
+    unsigned* mw = s_match + w * nbins;            // this warp's slots of set 0; set q is NS-strided by RS_WARPS * nbins
+    const int set_stride = RS_WARPS * nbins;
 #pragma unroll
-    for (int i = 0; i < IPT; i++) {
+    for (int i0 = 0; i0 < IPT; i0 += NS) {
         // lanes of this warp holding the same digit: OR the lane bits into the digit's slot (one ATOMS; MATCH.ANY
         // issues about once per 64 cycles per SM on sm_100 and alone bounded this kernel, eight ballots cost ~32
         // issue slots)
-        unsigned d = (((unsigned)key[i] - bias) >> shift) & mask;
-        atomicOr(&s_match[w][d], 1u << lane);
+        unsigned d[NS];
+#pragma unroll
+        for (int q = 0; q < NS; q++) {
+            d[q] = (((unsigned)key[i0 + q] - bias) >> shift) & mask;
+            atomicOr(&mw[q * set_stride + d[q]], 1u << lane);
+        }
         __syncwarp();
-        unsigned m = s_match[w][d];
-        int r = s_cnt[w][d] + __popc(m & lt);
-        rank[i] = (unsigned short)r;
+        unsigned own[NS];
+#pragma unroll
+        for (int j = 0; j < NS; j++) {
+            int r = s_cnt[w][d[j]];
+#pragma unroll
+            for (int q = 0; q < j; q++) r += __popc(mw[q * set_stride + d[j]]);     // same digit in the earlier items of the round
+            own[j] = mw[j * set_stride + d[j]];
+            rank[i0 + j] = (unsigned short)(r + __popc(own[j] & lt));
+        }
         __syncwarp();
-        if ((m >> lane) <= 1u) { s_cnt[w][d] = r + 1; s_match[w][d] = 0u; }   // highest lane of the group publishes the new count
+#pragma unroll
+        for (int j = 0; j < NS; j++) {
+            if ((own[j] >> lane) <= 1u) {          // highest lane of the group publishes the group size and clears the slot
+                if (NS == 1) s_cnt[w][d[j]] = (int)rank[i0 + j] + 1;
+                else atomicAdd(&s_cnt[w][d[j]], __popc(own[j]));
+                mw[j * set_stride + d[j]] = 0u;
+            }
+        }
         __syncwarp();
     }
     __syncthreads();
@@ -439,8 +464,15 @@ int rs_sort(const KeyT* keys_in, KeyT* keys_out, const unsigned* vals_in, unsign
         LGS_CHECK_LAUNCH("rs_hist_kernel");
         rs_scan_rows_kernel<<<nbins, RS_THREADS, 0, st>>>(table, p.nblocks, totals);
         LGS_CHECK_LAUNCH("rs_scan_rows_kernel");
-        if (p.ipt == 16) rs_scatter_kernel<KeyT, 16><<<p.nblocks, RS_THREADS, 0, st>>>(ksrc, vsrc, kdst, vdst, n, bit, nbins, p.nblocks, table, totals, bias, n_dev, bias_dev);
-        else rs_scatter_kernel<KeyT, 8><<<p.nblocks, RS_THREADS, 0, st>>>(ksrc, vsrc, kdst, vdst, n, bit, nbins, p.nblocks, table, totals, bias, n_dev, bias_dev);
+        // keys ranked per round: as many as the match slots fit in the value staging buffer they alias (env LGS_RS_RANK caps it: A/B)
+        static const int rank_cap = getenv("LGS_RS_RANK") ? atoi(getenv("LGS_RS_RANK")) : 2;   // measured: 172 / 166 / 172 us at 1 / 2 / 4 (profiles/rank_ab_r2.txt)
+        int ns = 1;
+        while (ns < 4 && ns * 2 <= rank_cap && ns * 2 * RS_WARPS * nbins <= p.tile) ns *= 2;
+#define RS_SCATTER(IPT_, NS_) rs_scatter_kernel<KeyT, IPT_, NS_><<<p.nblocks, RS_THREADS, 0, st>>>(ksrc, vsrc, kdst, vdst, n, bit, nbins, \
+                                                                                             p.nblocks, table, totals, bias, n_dev, bias_dev)
+        if (p.ipt == 16) { if (ns == 4) RS_SCATTER(16, 4); else if (ns == 2) RS_SCATTER(16, 2); else RS_SCATTER(16, 1); }
+        else { if (ns == 4) RS_SCATTER(8, 4); else if (ns == 2) RS_SCATTER(8, 2); else RS_SCATTER(8, 1); }
+#undef RS_SCATTER
         LGS_CHECK_LAUNCH("rs_scatter_kernel");
         ksrc = kdst; vsrc = vdst;
         bit += dbits;
