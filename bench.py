@@ -376,8 +376,8 @@ def ref_cuda_views_per_s(args, scene_np, iters=24):
 # counted in-run, so the issue roofline follows the workload and the clocks of THIS run
 ISSUE_MODEL = {
     # kernel: (warp instructions per (tile, splat) iteration, description of the unit)
-    "lgs_rasterize_backward": {"8x16": 155.3, "unit": "(tile, splat) iterations = sum over tiles of the deepest consumed list position",
-                               "source": "profiles/ncu_raster_r2a_v2_8x16.txt: 257.7 M warp instructions / 1.659 M iterations"},
+    "lgs_rasterize_backward": {"8x16": 135.7, "unit": "(tile, splat) iterations = sum over tiles of the deepest consumed list position",
+                               "source": "profiles/ncu_all_kernels_r2g_c2.txt launch 23: 225.07 M warp instructions / 1.659 M iterations"},
 }
 
 
