@@ -7,6 +7,11 @@
 // IEEE ones) in the reference's expression order, and 2*ln(255 o) is evaluated in double and rounded
 // once.  The reference's own build uses --use_fast_math here (GR/setup.py:35), which is why its lists
 // can differ from ours on pairs that graze a tile corner.
+// Attribution (carried over from the file this restates, GR/speedy_splat.cuh:1-13): the ellipse/tile overlap walk is the
+// "AccuTile" procedure of speedy-splat (https://github.com/j-alex-hanson/speedy-splat), itself based on "gaussian-splatting"
+// by Inria and the Max Planck Institut fuer Informatik (MPII).  Original work (c) Inria and MPII, licensed under the
+// Gaussian-Splatting License: use, reproduction and distribution of that work and its derivatives for non-commercial
+// research and evaluation purposes only.  See NOTICE.md at the repository root.
 #pragma once
 
 struct SplatGeom {

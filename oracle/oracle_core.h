@@ -535,6 +535,9 @@ static inline void SUF(splat_setup)(REAL ndcx, REAL ndcy, REAL viewz, REAL A, RE
     g->rect_max[1] = SUF(imax)(0, SUF(imin)(gy, SUF(f2i_rz)((g->bbox_max[1] + TH - 1) / TH)));
 }
 
+/* Attribution: the overlap walk restated below is speedy-splat's "AccuTile" procedure (https://github.com/j-alex-hanson/
+ * speedy-splat, based on Inria/MPII "gaussian-splatting", Gaussian-Splatting License, non-commercial research and evaluation
+ * use; notice carried over from GR/speedy_splat.cuh:1-13, see NOTICE.md). */
 /* GR/speedy_splat.cuh:33-149 ; returns the tile count, optionally emits (tile+1, idx) at keys/vals[off..] */
 static inline int SUF(process_tiles)(const SUF(splat_geom)* g, int TH, int TW, int gx,
                                      int32_t idx, int off, int cap, int32_t* keys, int32_t* vals)
