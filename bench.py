@@ -194,6 +194,9 @@ def camera_np(i, args):
 def stage_bytes(stats, S, K):
     """Algorithmic bytes per view and stage."""
     Nv, Nmax, D, P, Nvis = stats["Nv"], stats["Nmax"], stats["D"], stats["P"], stats["N_visible"]
+    # Gaussians whose record gradient is non-zero: project_backward reads every live slot's 48-byte record gradient but does the
+    # parameter work (geometry re-read, read-modify-write of the dense gradient rows) only for these
+    Ng = stats.get("N_grad", Nv)
     par = 4 * (3 + 3 + 4 + 3 * K + 1)
     bits_passes = stats["tile_sort_passes"]
     return {
@@ -209,7 +212,7 @@ def stage_bytes(stats, S, K):
         "lgs_tile_range_u16": 2 * D,
         "lgs_rasterize_forward_packed": 4 * D + 48 * Nvis + 18 * P,
         "lgs_rasterize_backward": 48 * Nmax + 4 * D + 48 * Nvis + 30 * P + 36 * Nvis,
-        "lgs_project_backward": 48 * Nv + 44 * Nv + par * Nv,
+        "lgs_project_backward": 48 * Nv + (44 + 2 * par) * Ng,
         "lgs_sparse_chunk_op": 3 * par * Nv,
     }
 
@@ -575,6 +578,16 @@ def run_ours(args, rank, world, local_rank):
                  "mean_contributors_per_pixel": float(st.last.view(torch.uint16).float().mean().item()),
                  "max_list_len": int(lens.max().item()), "mean_list_len": float(lens.float().mean().item()),
                  "backward_tile_splat_iterations": int(kmax_t.sum().item())}
+        try:
+            # how many Gaussians receive a gradient from this view (the others are behind saturated pixels): one un-timed backward
+            # with the bench's loss weights, count the non-zero 48-byte record gradients
+            d_pad = torch.zeros((1, 3, gy * th, gx * tw), dtype=torch.float32, device=dev)
+            d_pad[..., :H, :W] = w
+            _, pg = pipeline.render_view_backward(params, st, d_pad, accumulate_into=None)
+            stats["N_grad"] = int((pg[0, : st.n_chunks_visible * S] != 0).any(dim=1).sum().item())
+            del d_pad, pg
+        except Exception as e:                                   # statistics only: never fail the run over it
+            print(f"[bench] N_grad not measured ({e}); project_backward bytes use N_v", file=sys.stderr)
 
     # ---- e2e: host inputs, H2D + D2H inside the timed region ------------------------------------------
     e2e = None
@@ -765,7 +778,9 @@ def run_ours(args, rank, world, local_rank):
                               "unit": "T warp-inst/s", "frac": ach / peak_ips, "work_units_per_launch": work, "unit_of_work": im["unit"],
                               "warp_inst_per_unit": im[args.tile], "calibration": im["source"], "sm_count": sms,
                               "sm_mhz_in_run": clocks["sm_mhz"], "ms_per_launch": stages[dom]["ms_per_view"]}
-    path_bytes = sum(v for k, v in bytes_per.items())
+    # whole path = the stages this run actually launched (bytes_per also lists the variants that were not: 32-bit tile keys,
+    # the compacted-gradient scatter of level A)
+    path_bytes = sum(s_["alg_bytes"] for s_ in stages.values() if "alg_bytes" in s_)
     survey_bytes = 748 * stats["Nv"] + 172 * stats["D"] + 48 * stats["P"]
     ms_view = ms / (vpr * args.steps)
     ms_view_serial = ms_serial / (vpr * args.steps)
