@@ -77,21 +77,43 @@ def parse():
 # ---------------------------------------------------------------------------------------------------
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe).
+
+    nvidia-smi needs a few hundred ms to print its first line, longer than a short timed region, so the sampler is started before
+    the warm-up steps (the same workload) and every line carries nvidia-smi's own timestamp; stop() keeps the samples whose
+    timestamp falls between mark_begin() and mark_end() (host clock, taken right after the synchronising barriers that bracket
+    the timed region).  If none falls inside (very short runs) the samples taken under the warm-up load are reported and
+    ``window`` says so."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.idx, self.proc, self.path = gpu_index, None, None
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
             f = tempfile.NamedTemporaryFile(prefix="clocks_", suffix=".csv", delete=False)
             self.path = f.name
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.idx)], stdout=f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
+
+    @staticmethod
+    def _stamp(text):
+        """nvidia-smi prints local time as 'YYYY/MM/DD HH:MM:SS.mmm'."""
+        import datetime
+        try:
+            return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except Exception:
+            return None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -103,20 +125,30 @@ class ClockSampler:
         except Exception:
             pass
         try:
-            sm, mx, reasons = [], [], set()
+            rows = []                                   # (timestamp or None, sm, max, reasons)
             for line in open(self.path):
                 c = [x.strip() for x in line.split(",")]
-                if len(c) < 9:
+                if len(c) < 10:
                     continue
                 try:
-                    sm.append(float(c[1])); mx.append(float(c[2]))
+                    sm_, mx_ = float(c[2]), float(c[3])
                 except ValueError:
                     continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            if sm:
-                out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+                rs = {name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[6:10])
+                      if v.lower().startswith("active")}
+                rows.append((self._stamp(c[0]), sm_, mx_, rs))
+            inside = [r for r in rows if r[0] is not None and self.t_begin is not None and self.t_end is not None
+                      and self.t_begin <= r[0] <= self.t_end]
+            window = "timed region"
+            if not inside:
+                # nothing stamped inside the region: everything sampled since the sampler started (warm-up + timed region, same load)
+                inside, window = rows, "warm-up + timed region (no sample stamped inside the timed region)"
+            if inside:
+                reasons = set()
+                for r in inside:
+                    reasons |= r[3]
+                out = {"sm_mhz": float(np.median([r[1] for r in inside])), "sm_max_mhz": float(max(r[2] for r in inside)),
+                       "reasons": sorted(reasons), "samples": len(inside), "window": window, "samples_total": len(rows)}
             os.unlink(self.path)
         except Exception:
             pass
@@ -484,14 +516,15 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize(dev)
 
     # ---- value: inputs resident ------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                   # before the warm-up: nvidia-smi's first line takes longer than a short timed region
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record()
     for _ in range(args.steps):
         step(record=True)
@@ -499,6 +532,7 @@ def run_ours(args, rank, world, local_rank):
         a.wait()
     e1.record()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
     comm_ms = sum(a_.elapsed_time(b_) for a_, b_ in comm_events) / max(1, len(comm_events)) if comm_events else 0.0
