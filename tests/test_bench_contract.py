@@ -29,3 +29,61 @@ def test_metric_matches_baseline_json():
     base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
     src = open(os.path.join(ROOT, "bench.py")).read()
     assert base["metric"].split()[0] in src or "views" in src
+
+
+def _bench_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_clock_sampler_keeps_the_samples_stamped_inside_the_timed_region(tmp_path, monkeypatch):
+    """ClockSampler against a stand-in nvidia-smi that prints stamped CSV lines in nvidia-smi's format: only samples whose
+    timestamp lies between mark_begin() and mark_end() are reported; with none inside, the warm-up samples are and it says so;
+    a throttle reason seen inside the region is listed."""
+    import time
+    fake = tmp_path / "nvidia-smi"
+    fake.write_text("#!" + sys.executable + "\n"
+                    "import datetime, time\n"
+                    "n = 0\n"
+                    "while True:\n"
+                    "    t = datetime.datetime.now().strftime('%Y/%m/%d %H:%M:%S.%f')[:-3]\n"
+                    "    cap = 'Active' if n >= 12 else 'Not Active'\n"
+                    "    print(f'{t}, 0, 1965, 1965, 700.1, 0x0000000000000004, Not Active, Not Active, Not Active, {cap}', flush=True)\n"
+                    "    n += 1\n"
+                    "    time.sleep(0.02)\n")
+    fake.chmod(0o755)
+    monkeypatch.setenv("PATH", str(tmp_path) + os.pathsep + os.environ.get("PATH", ""))
+    bench = _bench_module()
+    s = bench.ClockSampler(0)
+    s.start()
+    time.sleep(0.6)
+    s.mark_begin()
+    time.sleep(0.3)
+    s.mark_end()
+    out = s.stop()
+    assert out["window"] == "timed region" and 5 <= out["samples"] < out["samples_total"]
+    assert out["sm_mhz"] == 1965.0 and out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"]
+    s = bench.ClockSampler(0)
+    s.start()
+    time.sleep(0.4)
+    s.mark_begin(); s.mark_end()
+    out = s.stop()
+    assert out["samples"] == out["samples_total"] > 0 and out["window"].startswith("warm-up")
+    assert bench.ClockSampler._stamp("2026/09/24 00:53:12.345") is not None and bench.ClockSampler._stamp("N/A") is None
+
+
+def test_path_bytes_count_only_the_launched_stages():
+    """stage_bytes lists every variant (16- and 32-bit tile keys, level A's scatter); the whole-path figure must be the sum over
+    the stages a run launched, and project_backward is charged on the Gaussians that carry a gradient."""
+    bench = _bench_module()
+    st = {"Nv": 984960, "Nmax": 1000064, "D": 10897674, "P": 2073600, "N_visible": 923397, "tiles": 16200, "tile_sort_passes": 2,
+          "N_grad": 108250}
+    b = bench.stage_bytes(st, 128, 16)
+    assert b["lgs_project_backward"] == 48 * st["Nv"] + (44 + 2 * 236) * st["N_grad"]
+    st2 = dict(st); del st2["N_grad"]
+    assert bench.stage_bytes(st2, 128, 16)["lgs_project_backward"] == 48 * st["Nv"] + (44 + 2 * 236) * st["Nv"]
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert "sum(v for k, v in bytes_per.items())" not in src
