@@ -123,7 +123,11 @@ class ClockSampler:
             self.proc.terminate()
             self.proc.wait(timeout=5)
         except Exception:
-            pass
+            try:                                        # never leave a polling nvidia-smi behind this process
+                self.proc.kill()
+                self.proc.wait(timeout=5)
+            except Exception:
+                pass
         try:
             rows = []                                   # (timestamp or None, sm, max, reasons)
             for line in open(self.path):
